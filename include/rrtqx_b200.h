@@ -1,0 +1,312 @@
+/*
+ * rrtqx_b200.h -- C ABI of librrtqx_b200.so: the B200 (sm_100a) implementation
+ * of RRTQX_3D's geometric inner loop (batched kd-tree neighbour queries and
+ * batched edge/node-vs-obstacle collision checks).
+ *
+ * This is the drop-in boundary.  The reference (Julia) has no FFI for this
+ * path today; each entry point below names the Julia function(s) whose work it
+ * takes over, as file:line under /root/reference/code_RRTQx_3D/.  The Julia
+ * binding a maintainer adds is julia/RRTQXGpu.jl; the
+ * Python ctypes mirror used by the tests is rrtqx_3d_b200/_abi.py.
+ *
+ * Conventions
+ *  - Every function returns rrtqx_status (0 = ok).  The message of the last
+ *    failure is available from rrtqx_last_error(ctx) (ctx may be NULL for
+ *    failures of rrtqx_ctx_create).  The reference signals errors with Julia
+ *    error(...) exceptions; the Julia wrapper re-raises non-zero statuses.
+ *  - Plain pointers and sizes only.  Input/output array pointers may be host
+ *    (pageable or pinned) or CUDA device pointers; the library detects which
+ *    (cudaPointerGetAttributes) and copies only when needed.  Arrays are
+ *    row-major: an n x d position array is n consecutive rows of d doubles,
+ *    which is the memory image of Julia's 1xd `position` matrices stacked.
+ *  - Node indices are 0-based int32 in insertion order (index i = the i-th
+ *    kdInsert).  Julia wrappers add 1.
+ *  - Single caller thread per context, blocking calls (results are ready on
+ *    return) unless a function says "async".  There is NO CPU fallback: if no
+ *    CUDA device is usable, rrtqx_ctx_create fails with RRTQX_ERR_CUDA.
+ *  - All arithmetic that decides membership / collision is IEEE binary64 in
+ *    the reference's operation order, never fused.
+ */
+#ifndef RRTQX_B200_H
+#define RRTQX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RRTQX_API __declspec(dllexport)
+#else
+#define RRTQX_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t rrtqx_status;
+enum {
+  RRTQX_OK = 0,
+  RRTQX_ERR_INVALID = 1,     /* bad argument */
+  RRTQX_ERR_CUDA = 2,        /* CUDA runtime / no device */
+  RRTQX_ERR_NOMEM = 3,       /* device or host allocation failed */
+  RRTQX_ERR_EMPTY_TREE = 4,  /* query on an empty tree (the reference would
+                                dereference an undefined root,
+                                kdTree_general.jl:359,895) */
+  RRTQX_ERR_UNSUPPORTED = 5,
+  RRTQX_ERR_STATE = 6        /* result object not filled yet, etc. */
+};
+
+typedef struct rrtqx_ctx rrtqx_ctx;
+typedef struct rrtqx_tree rrtqx_tree;
+typedef struct rrtqx_spheres rrtqx_spheres;
+typedef struct rrtqx_polygons rrtqx_polygons;
+typedef struct rrtqx_edges rrtqx_edges;
+typedef struct rrtqx_range_result rrtqx_range_result;
+typedef struct rrtqx_sweep_result rrtqx_sweep_result;
+
+/* ---------------------------------------------------------------- context */
+
+RRTQX_API const char *rrtqx_version(void);
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to launch on (e.g. the
+ * caller's current stream) or NULL for a private non-blocking stream. */
+RRTQX_API rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream,
+                                        rrtqx_ctx **out);
+RRTQX_API rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx);
+RRTQX_API const char *rrtqx_last_error(const rrtqx_ctx *ctx);
+RRTQX_API rrtqx_status rrtqx_ctx_sync(rrtqx_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+RRTQX_API rrtqx_status rrtqx_ctx_kernel_launches(const rrtqx_ctx *ctx,
+                                                 int64_t *out);
+/* CUDA-event timing of the context's most recent named phase, in ms; phase is
+ * one of "range_query", "nearest", "edge_check", "node_check", "add_sweep",
+ * "remove_sweep", "tree_build".  Measured on the context's stream. */
+RRTQX_API rrtqx_status rrtqx_ctx_last_phase_ms(rrtqx_ctx *ctx,
+                                               const char *phase, float *ms);
+
+/* ------------------------------------------------------------------- tree */
+/* KDTree{T}(d, f) / KDTree{T}(d, f, wraps, wrapPoints)
+ * (kdTree_general.jl:94-112).  The metric f is always KDdist = euclidianDist
+ * in both edge files (DRRT_SimpleEdge_functions.jl:51,
+ * DRRT_DubinsEdge_functions.jl:52), so it is not a parameter.  d in 2..4.
+ * wraps: 0-based dimension indices that wrap around, period wrap_points[i]
+ * (space assumed to start at 0, kdTree_general.jl:101-102). */
+RRTQX_API rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d,
+                                         int32_t num_wraps,
+                                         const int32_t *wraps,
+                                         const double *wrap_points,
+                                         rrtqx_tree **out);
+RRTQX_API rrtqx_status rrtqx_tree_destroy(rrtqx_tree *tree);
+/* kdInsert (kdTree_general.jl:121-170) for n nodes in order.  The resulting
+ * kd topology (parent / children / split) is exactly the one sequential
+ * insertion produces.  *first_index_out = index of positions[0]. */
+RRTQX_API rrtqx_status rrtqx_tree_insert_batch(rrtqx_tree *tree,
+                                               const double *positions,
+                                               int64_t n,
+                                               int32_t *first_index_out);
+/* kdInsert of one node (the planner's per-iteration insert, DRRT_Q.jl:2575). */
+RRTQX_API rrtqx_status rrtqx_tree_insert(rrtqx_tree *tree,
+                                         const double *position,
+                                         int32_t *index_out);
+RRTQX_API rrtqx_status rrtqx_tree_size(const rrtqx_tree *tree, int64_t *n);
+/* kd fields of nodes [first, first+count) so the caller can keep
+ * RRTNode.kdParent/kdChildL/kdChildR/kdSplit populated
+ * (DRRT_data_structures.jl:25-33,68-72).  -1 = absent; split is 0-based.
+ * Any output pointer may be NULL. */
+RRTQX_API rrtqx_status rrtqx_tree_kd_fields(rrtqx_tree *tree, int64_t first,
+                                            int64_t count, int32_t *parent,
+                                            int32_t *child_l, int32_t *child_r,
+                                            int32_t *split);
+/* Copies positions of nodes [first, first+count) back (row-major). */
+RRTQX_API rrtqx_status rrtqx_tree_positions(rrtqx_tree *tree, int64_t first,
+                                            int64_t count, double *out);
+/* Tuning knob of the device index: mean points per grid cell the next
+ * (re)build aims for (default 8).  Does not change any result. */
+RRTQX_API rrtqx_status rrtqx_tree_set_cell_occupancy(rrtqx_tree *tree,
+                                                     double points_per_cell);
+/* Force the device index to absorb the unsorted tail of recent inserts now. */
+RRTQX_API rrtqx_status rrtqx_tree_reindex(rrtqx_tree *tree);
+
+/* -------------------------------------------------------- range queries */
+/* kdFindWithinRange(tree, range, q) (kdTree_general.jl:889-919), batched.
+ * For each query: every node with euclid(q,node) < range (strict), the root
+ * (node 0) being admitted with <= (:896-898); with wrap dimensions also the
+ * nodes within range of the ghost identities (ghostPoint.jl:60-111), keyed by
+ * the first identity that reaches them.  `ranges` = one radius per query, or
+ * NULL to use `range` for all.  The result lives on the device inside *result
+ * (created when *result == NULL, otherwise reused).  The per-query lists are
+ * SETS: their order is the device traversal order, not the reference's LIFO
+ * order. */
+enum {
+  RRTQX_RANGE_WANT_DIST = 1u, /* also produce the JList keys (distances) */
+  RRTQX_RANGE_COUNT_ONLY = 2u /* only counts and total */
+};
+RRTQX_API rrtqx_status rrtqx_range_query_batch(rrtqx_tree *tree,
+                                               const double *queries,
+                                               int64_t n_queries, double range,
+                                               const double *ranges,
+                                               uint32_t flags,
+                                               rrtqx_range_result **result,
+                                               int64_t *total_out);
+RRTQX_API rrtqx_status rrtqx_range_result_destroy(rrtqx_range_result *r);
+RRTQX_API rrtqx_status rrtqx_range_result_sizes(const rrtqx_range_result *r,
+                                                int64_t *n_queries,
+                                                int64_t *total);
+/* counts[q] (int32, n_queries) and offsets[q] (int64, n_queries): query q's
+ * list is idx[offsets[q] .. offsets[q]+counts[q]).  Lists are disjoint and
+ * tightly packed (sum counts == total).  Output pointers: host or device. */
+RRTQX_API rrtqx_status rrtqx_range_result_layout(rrtqx_range_result *r,
+                                                 int32_t *counts,
+                                                 int64_t *offsets);
+/* idx (int32, total) and dist (double, total; NULL allowed).  dist requires
+ * RRTQX_RANGE_WANT_DIST at query time. */
+RRTQX_API rrtqx_status rrtqx_range_result_fetch(rrtqx_range_result *r,
+                                                int32_t *idx, double *dist);
+/* Device views (valid until the result is reused or destroyed). */
+RRTQX_API rrtqx_status rrtqx_range_result_device(const rrtqx_range_result *r,
+                                                 const int32_t **counts,
+                                                 const int64_t **offsets,
+                                                 const int32_t **idx,
+                                                 const double **dist);
+
+/* kdFindNearest(tree, q) (kdTree_general.jl:357-385), batched: index and
+ * distance of the nearest node (ghost identities included).  On exact
+ * distance ties the reference returns the first minimiser in its traversal
+ * order; this library returns the minimiser with the smallest index
+ * (documented tie).  The distance is bit-exact. */
+RRTQX_API rrtqx_status rrtqx_nearest_batch(rrtqx_tree *tree,
+                                           const double *queries,
+                                           int64_t n_queries, int32_t *idx_out,
+                                           double *dist_out);
+
+/* ------------------------------------------------------- sphere obstacles */
+/* CSpace.obstacles :: List{SphereObstacle} (DRRT_data_structures.jl:267-316)
+ * flattened: centres n x 3, radii n, active n (uint8).  active[i] must be
+ * !(obstacleUnused || lifeSpan <= 0), the early-out predicate of
+ * explicitEdgeCheck3D / explicitPointCheck2D (DRRT_Q.jl:1777,1467). */
+RRTQX_API rrtqx_status rrtqx_spheres_create(rrtqx_ctx *ctx,
+                                            rrtqx_spheres **out);
+RRTQX_API rrtqx_status rrtqx_spheres_destroy(rrtqx_spheres *s);
+RRTQX_API rrtqx_status rrtqx_spheres_upload(rrtqx_spheres *s,
+                                            const double *centers,
+                                            const double *radii,
+                                            const uint8_t *active, int64_t n);
+/* In-place update of obstacles [first, first+count): radius (obstacle
+ * augmentation, obstacleAugmentation.jl:106-114) and/or active flag.  Either
+ * pointer may be NULL. */
+RRTQX_API rrtqx_status rrtqx_spheres_update(rrtqx_spheres *s, int64_t first,
+                                            int64_t count, const double *radii,
+                                            const uint8_t *active);
+RRTQX_API rrtqx_status rrtqx_spheres_size(const rrtqx_spheres *s, int64_t *n);
+
+/* ------------------------------------------------------ collision checks */
+enum {
+  RRTQX_CHECK_FMA_DOT = 1u,       /* evaluate the 3-term dot of
+                                     distancePointToSegment with fused
+                                     multiply-adds (OpenBLAS build variant,
+                                     SURVEY.md 8c); default unfused */
+  RRTQX_CHECK_IGNORE_ACTIVE = 2u, /* treat every obstacle as active */
+  RRTQX_CHECK_QUICK_PASS = 4u     /* node check: run the quickCheck pass first
+                                     (explicitPointCheck, DRRT_Q.jl:1520) as
+                                     opposed to explicitPointCheck3D (:1558) */
+};
+/* explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826) for SimpleEdge
+ * (DRRT_SimpleEdge_functions.jl:210 -> explicitEdgeCheck3D DRRT_Q.jl:1775 ->
+ * distancePointToSegment :1205), batched over edges between tree nodes:
+ * collide_out[e] = OR over all active spheres.  Edge e runs from node src[e]
+ * to node dst[e]; the test is NOT symmetric in (src,dst). */
+RRTQX_API rrtqx_status rrtqx_edge_check_batch(rrtqx_tree *tree,
+                                              const rrtqx_spheres *spheres,
+                                              const int32_t *src,
+                                              const int32_t *dst,
+                                              int64_t n_edges,
+                                              double robot_radius,
+                                              uint32_t flags,
+                                              uint8_t *collide_out);
+/* Same for segments given by explicit end points (a sample that is not in the
+ * tree yet, the robot edge R.robotEdge DRRT_Q.jl:3287): starts/ends n x 3. */
+RRTQX_API rrtqx_status rrtqx_segment_check_batch(rrtqx_ctx *ctx,
+                                                 const rrtqx_spheres *spheres,
+                                                 const double *starts,
+                                                 const double *ends,
+                                                 int64_t n_segments,
+                                                 double robot_radius,
+                                                 uint32_t flags,
+                                                 uint8_t *collide_out);
+/* explicitPointCheck / explicitNodeCheck (DRRT_Q.jl:1520-1556,1594) and the
+ * 3D twins (:1558-1590,1595), batched: collide_out[i] and the certificate
+ * cert_out[i] (min clearance; 0.0 on collision; NULL allowed). points n x 3. */
+RRTQX_API rrtqx_status rrtqx_node_check_batch(rrtqx_ctx *ctx,
+                                              const rrtqx_spheres *spheres,
+                                              const double *points, int64_t n,
+                                              double robot_radius,
+                                              uint32_t flags,
+                                              uint8_t *collide_out,
+                                              double *cert_out);
+
+/* ------------------------------------------------- resident edge set + sweeps */
+/* Device mirror of the planner's out-edge lists: for node v the reference
+ * iterates InitialNeighborListOut then rrtNeighborsOut
+ * (DRRT_Q.jl:2408-2431); the caller uploads those edges as (src,dst) pairs in
+ * any order (edge id = position in the upload) and optionally parent[v]
+ * (index of rrtParentEdge.endNode, -1 when !rrtParentUsed). */
+RRTQX_API rrtqx_status rrtqx_edges_create(rrtqx_tree *tree, rrtqx_edges **out);
+RRTQX_API rrtqx_status rrtqx_edges_destroy(rrtqx_edges *e);
+RRTQX_API rrtqx_status rrtqx_edges_upload(rrtqx_edges *e, const int32_t *src,
+                                          const int32_t *dst, int64_t n_edges,
+                                          const int32_t *parent,
+                                          int64_t n_parent);
+RRTQX_API rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges);
+
+/* addNewObstacle (DRRT_Q.jl:3220-3290) geometric part, batched over obstacles
+ * ob_ids[0..n_obs) of `spheres` (treated as active, :3222).  For obstacle o:
+ * candidate nodes = kdFindWithinRange(KD, (robot_radius+delta)+radius_o,
+ * centre_o) (:3195-3204); every out-edge of a candidate that collides with o
+ * is "blocked" (edge.dist = Inf, :3248-3249); every candidate whose parent
+ * edge collides is an "orphan" (:3257-3270).  Only edges whose START node is
+ * a candidate are tested, as in the reference.
+ * Results (OR over the given obstacles): the set of blocked edge ids, the set
+ * of orphaned node ids, and the same as per-edge / per-node byte flags. */
+RRTQX_API rrtqx_status rrtqx_obstacle_add_sweep(rrtqx_edges *edges,
+                                                const rrtqx_spheres *spheres,
+                                                const int32_t *ob_ids,
+                                                int64_t n_obs,
+                                                double robot_radius,
+                                                double delta, uint32_t flags,
+                                                rrtqx_sweep_result **result);
+/* removeObstacle (DRRT_Q.jl:3295-3362, DRRT.jl:3202-3268) geometric part for
+ * ONE obstacle ob_id.  edge_dist_inf[e] = (edge.dist == Inf).  An edge is
+ * "restored" if it is flagged, collides with ob_id and with none of the
+ * obstacles in other_ids (the caller evaluates the reference's time-window
+ * predicate :3330 to build that list).  QX behaviour (obstacle disabled before
+ * the loop, nothing restored) is the caller passing
+ * RRTQX_SWEEP_REMOVED_INACTIVE. */
+enum { RRTQX_SWEEP_REMOVED_INACTIVE = 16u };
+RRTQX_API rrtqx_status rrtqx_obstacle_remove_sweep(
+    rrtqx_edges *edges, const rrtqx_spheres *spheres, int32_t ob_id,
+    const int32_t *other_ids, int64_t n_others, const uint8_t *edge_dist_inf,
+    double robot_radius, double delta, uint32_t flags,
+    rrtqx_sweep_result **result);
+RRTQX_API rrtqx_status rrtqx_sweep_result_destroy(rrtqx_sweep_result *r);
+/* n_edge_hits = number of distinct edges reported (blocked / restored),
+ * n_node_hits = number of distinct nodes reported (orphans / requeue),
+ * n_candidates = sum over obstacles of candidate nodes (start-node filter),
+ * n_pair_tests = (edge, obstacle) pairs that passed the start-node filter, the
+ * "edge checks" unit of BASELINE.json (parent edges included). */
+RRTQX_API rrtqx_status rrtqx_sweep_result_sizes(const rrtqx_sweep_result *r,
+                                                int64_t *n_edge_hits,
+                                                int64_t *n_node_hits,
+                                                int64_t *n_candidates,
+                                                int64_t *n_pair_tests);
+/* ascending edge ids (n_edge_hits) and node ids (n_node_hits).  Pointers:
+ * host or device, NULL ok. */
+RRTQX_API rrtqx_status rrtqx_sweep_result_fetch(rrtqx_sweep_result *r,
+                                                int32_t *edge_ids,
+                                                int32_t *node_ids);
+/* byte flags: edge_flag[e] (n_edges), node_flag[v] (nodes at edge upload). */
+RRTQX_API rrtqx_status rrtqx_sweep_result_flags(rrtqx_sweep_result *r,
+                                                uint8_t *edge_flag,
+                                                uint8_t *node_flag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTQX_B200_H */

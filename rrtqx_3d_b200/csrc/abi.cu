@@ -1,0 +1,574 @@
+// abi.cu -- extern "C" boundary of librrtqx_b200.so (include/rrtqx_b200.h).
+// Every entry point converts C++ exceptions into a status + message; there is
+// no CPU fallback anywhere behind this file.
+#include <mutex>
+
+#include "objects.cuh"
+
+using namespace rrtqx;
+
+static thread_local std::string g_last_error;
+
+struct NearestScratchHolder {
+  rrtqx_range_result sortbuf;
+  DevBuf<int32_t> idx;
+  DevBuf<double> dist;
+};
+static std::map<rrtqx_tree *, NearestScratchHolder *> g_nearest_scratch;
+static std::mutex g_nearest_mutex;
+
+namespace {
+template <typename F>
+rrtqx_status guarded(rrtqx_ctx *ctx, F &&f) {
+  try {
+    f();
+    return RRTQX_OK;
+  } catch (const Error &e) {
+    g_last_error = e.what();
+    if (ctx) ctx->err = e.what();
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    g_last_error = "host allocation failed";
+    if (ctx) ctx->err = g_last_error;
+    return RRTQX_ERR_NOMEM;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (ctx) ctx->err = e.what();
+    return RRTQX_ERR_INVALID;
+  }
+}
+void bind_device(rrtqx_ctx *ctx) { RQ_CUDA(cudaSetDevice(ctx->device)); }
+}  // namespace
+
+extern "C" {
+
+const char *rrtqx_version(void) { return "rrtqx-b200 0.1 (sm_100a)"; }
+
+rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream, rrtqx_ctx **out) {
+  return guarded(nullptr, [&] {
+    RQ_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw Error(RRTQX_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    RQ_REQUIRE(device >= 0 && device < count, "device ordinal out of range");
+    RQ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw Error(RRTQX_ERR_CUDA, std::string("this library is built for sm_100a only; device is ") + prop.name);
+    rrtqx_ctx *c = new rrtqx_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+      c->stream = (cudaStream_t)cuda_stream;
+      c->own_stream = false;
+    } else {
+      RQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->own_stream = true;
+    }
+    *out = c;
+  });
+}
+
+rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx) {
+  if (!ctx) return RRTQX_OK;
+  return guarded(nullptr, [&] {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->phases) {
+      if (kv.second.a) cudaEventDestroy(kv.second.a);
+      if (kv.second.b) cudaEventDestroy(kv.second.b);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+const char *rrtqx_last_error(const rrtqx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+rrtqx_status rrtqx_ctx_sync(rrtqx_ctx *ctx) {
+  if (!ctx) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] { bind_device(ctx); RQ_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+rrtqx_status rrtqx_ctx_kernel_launches(const rrtqx_ctx *ctx, int64_t *out) {
+  if (!ctx || !out) return RRTQX_ERR_INVALID;
+  *out = ctx->launches;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_ctx_last_phase_ms(rrtqx_ctx *ctx, const char *phase, float *ms) {
+  if (!ctx) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    RQ_REQUIRE(phase && ms, "NULL argument");
+    auto it = ctx->phases.find(phase);
+    if (it == ctx->phases.end() || !it->second.valid) throw Error(RRTQX_ERR_STATE, "phase has not run");
+    RQ_CUDA(cudaEventSynchronize(it->second.b));
+    RQ_CUDA(cudaEventElapsedTime(ms, it->second.a, it->second.b));
+  });
+}
+
+// ------------------------------------------------------------------- tree
+rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d, int32_t num_wraps, const int32_t *wraps,
+                               const double *wrap_points, rrtqx_tree **out) {
+  if (!ctx) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    RQ_REQUIRE(out != nullptr, "out is NULL");
+    RQ_REQUIRE(d >= 2 && d <= MAX_D, "d must be 2, 3 or 4");
+    RQ_REQUIRE(num_wraps >= 0 && num_wraps <= MAX_WRAPS, "num_wraps out of range");
+    RQ_REQUIRE(num_wraps == 0 || (wraps && wrap_points), "wraps / wrap_points is NULL");
+    rrtqx_tree *t = new rrtqx_tree();
+    t->ctx = ctx;
+    t->d = d;
+    t->wrap.num_wraps = num_wraps;
+    for (int i = 0; i < num_wraps; ++i) {
+      if (wraps[i] < 0 || wraps[i] >= d) { delete t; throw Error(RRTQX_ERR_INVALID, "wrap dimension out of range"); }
+      t->wrap.wraps[i] = wraps[i];
+      t->wrap.wrap_points[i] = wrap_points[i];
+    }
+    *out = t;
+  });
+}
+
+rrtqx_status rrtqx_tree_destroy(rrtqx_tree *tree) {
+  if (!tree) return RRTQX_OK;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+      std::lock_guard<std::mutex> lk(g_nearest_mutex);
+      auto it = g_nearest_scratch.find(tree);
+      if (it != g_nearest_scratch.end()) { delete it->second; g_nearest_scratch.erase(it); }
+    }
+    delete tree;
+  });
+}
+
+rrtqx_status rrtqx_tree_insert_batch(rrtqx_tree *tree, const double *positions, int64_t n, int32_t *first_index_out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  return guarded(tree->ctx, [&] {
+    bind_device(tree->ctx);
+    RQ_REQUIRE(n >= 0, "n is negative");
+    RQ_REQUIRE(positions != nullptr || n == 0, "positions is NULL");
+    if (first_index_out) *first_index_out = (int32_t)tree->n;
+    tree_insert_batch(tree, positions, n);
+    RQ_CUDA(cudaStreamSynchronize(tree->ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_tree_insert(rrtqx_tree *tree, const double *position, int32_t *index_out) {
+  return rrtqx_tree_insert_batch(tree, position, 1, index_out);
+}
+
+rrtqx_status rrtqx_tree_size(const rrtqx_tree *tree, int64_t *n) {
+  if (!tree || !n) return RRTQX_ERR_INVALID;
+  *n = tree->n;
+  return RRTQX_OK;
+}
+
+__global__ void kd_fields_kernel(const unsigned *__restrict__ child, const int32_t *__restrict__ parent,
+                                 const int8_t *__restrict__ split, int64_t first, int64_t count,
+                                 int32_t *__restrict__ o_parent, int32_t *__restrict__ o_l, int32_t *__restrict__ o_r,
+                                 int32_t *__restrict__ o_split) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  int64_t i = first + k;
+  o_parent[k] = parent[i];
+  unsigned l = child[2 * i], r = child[2 * i + 1];
+  o_l[k] = (l == KD_EMPTY) ? -1 : (int32_t)l;
+  o_r[k] = (r == KD_EMPTY) ? -1 : (int32_t)r;
+  o_split[k] = split[i];
+}
+
+__global__ void positions_kernel(const double4 *__restrict__ pos, int d, int64_t first, int64_t count,
+                                 double *__restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double4 p = pos[first + k];
+  double *o = out + k * d;
+  o[0] = p.x;
+  o[1] = p.y;
+  if (d >= 3) o[2] = p.z;
+  if (d >= 4) o[3] = p.w;
+}
+
+rrtqx_status rrtqx_tree_kd_fields(rrtqx_tree *tree, int64_t first, int64_t count, int32_t *parent, int32_t *child_l,
+                                  int32_t *child_r, int32_t *split) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(first >= 0 && count >= 0 && first + count <= tree->n, "node range out of bounds");
+    if (count == 0) return;
+    cudaStream_t st = ctx->stream;
+    ctx->stage_i32a.ensure((size_t)count * 4, st);
+    int32_t *b = ctx->stage_i32a.p;
+    kd_fields_kernel<<<div_up(count, 256), 256, 0, st>>>(tree->child.p, tree->parent.p, tree->split.p, first, count, b,
+                                                         b + count, b + 2 * count, b + 3 * count);
+    post_launch(ctx);
+    from_device(ctx, parent, b, (size_t)count);
+    from_device(ctx, child_l, b + count, (size_t)count);
+    from_device(ctx, child_r, b + 2 * count, (size_t)count);
+    from_device(ctx, split, b + 3 * count, (size_t)count);
+    RQ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+rrtqx_status rrtqx_tree_positions(rrtqx_tree *tree, int64_t first, int64_t count, double *out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(first >= 0 && count >= 0 && first + count <= tree->n, "node range out of bounds");
+    RQ_REQUIRE(out != nullptr || count == 0, "out is NULL");
+    if (count == 0) return;
+    cudaStream_t st = ctx->stream;
+    ctx->stage_f64.ensure((size_t)count * tree->d, st);
+    positions_kernel<<<div_up(count, 256), 256, 0, st>>>(tree->pos.p, tree->d, first, count, ctx->stage_f64.p);
+    post_launch(ctx);
+    from_device(ctx, out, ctx->stage_f64.p, (size_t)count * tree->d);
+    RQ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+rrtqx_status rrtqx_tree_set_cell_occupancy(rrtqx_tree *tree, double points_per_cell) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  return guarded(tree->ctx, [&] {
+    RQ_REQUIRE(points_per_cell > 0.0 && points_per_cell <= 4096.0, "points_per_cell out of range");
+    tree->occupancy = points_per_cell;
+  });
+}
+
+rrtqx_status rrtqx_tree_reindex(rrtqx_tree *tree) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  return guarded(tree->ctx, [&] {
+    bind_device(tree->ctx);
+    tree_reindex(tree);
+    RQ_CUDA(cudaStreamSynchronize(tree->ctx->stream));
+  });
+}
+
+// ---------------------------------------------------------- range / nearest
+rrtqx_status rrtqx_range_query_batch(rrtqx_tree *tree, const double *queries, int64_t n_queries, double range,
+                                     const double *ranges, uint32_t flags, rrtqx_range_result **result,
+                                     int64_t *total_out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(result != nullptr, "result is NULL");
+    RQ_REQUIRE(queries != nullptr || n_queries == 0, "queries is NULL");
+    if (!*result) {
+      *result = new rrtqx_range_result();
+      (*result)->ctx = ctx;
+    }
+    range_query(tree, queries, n_queries, range, ranges, flags, *result);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (total_out) *total_out = (*result)->total;
+  });
+}
+
+rrtqx_status rrtqx_range_result_destroy(rrtqx_range_result *r) {
+  if (!r) return RRTQX_OK;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    if (ctx) { bind_device(ctx); RQ_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    delete r;
+  });
+}
+
+rrtqx_status rrtqx_range_result_sizes(const rrtqx_range_result *r, int64_t *n_queries, int64_t *total) {
+  if (!r) return RRTQX_ERR_INVALID;
+  if (n_queries) *n_queries = r->n_queries;
+  if (total) *total = r->total;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_range_result_layout(rrtqx_range_result *r, int32_t *counts, int64_t *offsets) {
+  if (!r) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    from_device(ctx, counts, r->counts.p, (size_t)r->n_queries);
+    from_device(ctx, offsets, r->offsets.p, (size_t)r->n_queries);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_range_result_fetch(rrtqx_range_result *r, int32_t *idx, double *dist) {
+  if (!r) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    if (!r->has_lists) throw Error(RRTQX_ERR_STATE, "result holds counts only (RRTQX_RANGE_COUNT_ONLY)");
+    if (dist && !r->has_dist) throw Error(RRTQX_ERR_STATE, "distances were not requested (RRTQX_RANGE_WANT_DIST)");
+    from_device(ctx, idx, r->idx.p, (size_t)r->total);
+    from_device(ctx, dist, r->dist.p, (size_t)r->total);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_range_result_device(const rrtqx_range_result *r, const int32_t **counts, const int64_t **offsets,
+                                       const int32_t **idx, const double **dist) {
+  if (!r) return RRTQX_ERR_INVALID;
+  if (counts) *counts = r->counts.p;
+  if (offsets) *offsets = r->offsets.p;
+  if (idx) *idx = r->has_lists ? r->idx.p : nullptr;
+  if (dist) *dist = r->has_dist ? r->dist.p : nullptr;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_nearest_batch(rrtqx_tree *tree, const double *queries, int64_t n_queries, int32_t *idx_out,
+                                 double *dist_out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(queries != nullptr || n_queries == 0, "queries is NULL");
+    NearestScratchHolder *h;
+    {
+      std::lock_guard<std::mutex> lk(g_nearest_mutex);
+      auto it = g_nearest_scratch.find(tree);
+      if (it == g_nearest_scratch.end()) it = g_nearest_scratch.emplace(tree, new NearestScratchHolder()).first;
+      h = it->second;
+      h->sortbuf.ctx = ctx;
+    }
+    nearest_query(tree, &h->sortbuf, queries, n_queries, idx_out, dist_out, h->idx, h->dist);
+  });
+}
+
+// ---------------------------------------------------------------- spheres
+rrtqx_status rrtqx_spheres_create(rrtqx_ctx *ctx, rrtqx_spheres **out) {
+  if (!ctx) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    RQ_REQUIRE(out != nullptr, "out is NULL");
+    rrtqx_spheres *s = new rrtqx_spheres();
+    s->ctx = ctx;
+    *out = s;
+  });
+}
+
+rrtqx_status rrtqx_spheres_destroy(rrtqx_spheres *s) {
+  if (!s) return RRTQX_OK;
+  rrtqx_ctx *ctx = s->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    delete s;
+  });
+}
+
+__global__ void spheres_pack_kernel(const double *__restrict__ centers, const double *__restrict__ radii, int64_t first,
+                                    int64_t n, double4 *__restrict__ rec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 r = rec[first + i];
+  if (centers) { r.x = centers[3 * i]; r.y = centers[3 * i + 1]; r.z = centers[3 * i + 2]; }
+  if (radii) r.w = radii[i];
+  rec[first + i] = r;
+}
+
+rrtqx_status rrtqx_spheres_upload(rrtqx_spheres *s, const double *centers, const double *radii, const uint8_t *active,
+                                  int64_t n) {
+  if (!s) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = s->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(n >= 0 && n < (1 << 24), "n out of range");
+    RQ_REQUIRE(n == 0 || (centers && radii), "centers / radii is NULL");
+    cudaStream_t st = ctx->stream;
+    s->rec.ensure((size_t)n + 1, st);
+    s->active.ensure((size_t)n + 1, st);
+    s->n = n;
+    if (n == 0) return;
+    const double *dc = to_device(ctx, centers, (size_t)n * 3, ctx->stage_f64);
+    const double *dr = to_device(ctx, radii, (size_t)n, ctx->stage_f64b);
+    spheres_pack_kernel<<<div_up(n, 256), 256, 0, st>>>(dc, dr, 0, n, s->rec.p);
+    post_launch(ctx);
+    if (active) RQ_CUDA(cudaMemcpyAsync(s->active.p, active, (size_t)n, cudaMemcpyDefault, st));
+    else RQ_CUDA(cudaMemsetAsync(s->active.p, 1, (size_t)n, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+rrtqx_status rrtqx_spheres_update(rrtqx_spheres *s, int64_t first, int64_t count, const double *radii,
+                                  const uint8_t *active) {
+  if (!s) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = s->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "obstacle range out of bounds");
+    if (count == 0) return;
+    cudaStream_t st = ctx->stream;
+    if (radii) {
+      const double *dr = to_device(ctx, radii, (size_t)count, ctx->stage_f64b);
+      spheres_pack_kernel<<<div_up(count, 256), 256, 0, st>>>(nullptr, dr, first, count, s->rec.p);
+      post_launch(ctx);
+    }
+    if (active) RQ_CUDA(cudaMemcpyAsync(s->active.p + first, active, (size_t)count, cudaMemcpyDefault, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+rrtqx_status rrtqx_spheres_size(const rrtqx_spheres *s, int64_t *n) {
+  if (!s || !n) return RRTQX_ERR_INVALID;
+  *n = s->n;
+  return RRTQX_OK;
+}
+
+// ------------------------------------------------------------ collision
+rrtqx_status rrtqx_edge_check_batch(rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                                    const int32_t *dst, int64_t n_edges, double robot_radius, uint32_t flags,
+                                    uint8_t *collide_out) {
+  if (!tree || !spheres) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(tree->d == 3, "SimpleEdge checks need a 3-D tree (explicitEdgeCheck3D)");
+    RQ_REQUIRE(n_edges >= 0, "n_edges is negative");
+    RQ_REQUIRE(n_edges == 0 || (src && dst && collide_out), "NULL array");
+    if (n_edges && !is_device_ptr(src))
+      for (int64_t e = 0; e < n_edges; ++e)
+        RQ_REQUIRE(src[e] >= 0 && src[e] < tree->n && dst[e] >= 0 && dst[e] < tree->n, "edge endpoint out of range");
+    edge_check(ctx, tree, spheres, src, dst, nullptr, nullptr, n_edges, robot_radius, flags, collide_out);
+  });
+}
+
+rrtqx_status rrtqx_segment_check_batch(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *starts,
+                                       const double *ends, int64_t n_segments, double robot_radius, uint32_t flags,
+                                       uint8_t *collide_out) {
+  if (!ctx || !spheres) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(n_segments >= 0, "n_segments is negative");
+    RQ_REQUIRE(n_segments == 0 || (starts && ends && collide_out), "NULL array");
+    edge_check(ctx, nullptr, spheres, nullptr, nullptr, starts, ends, n_segments, robot_radius, flags, collide_out);
+  });
+}
+
+rrtqx_status rrtqx_node_check_batch(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *points, int64_t n,
+                                    double robot_radius, uint32_t flags, uint8_t *collide_out, double *cert_out) {
+  if (!ctx || !spheres) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(n >= 0, "n is negative");
+    RQ_REQUIRE(n == 0 || (points && collide_out), "NULL array");
+    node_check(ctx, spheres, points, n, robot_radius, flags, collide_out, cert_out);
+  });
+}
+
+// ------------------------------------------------------------ edges + sweeps
+rrtqx_status rrtqx_edges_create(rrtqx_tree *tree, rrtqx_edges **out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  return guarded(tree->ctx, [&] {
+    RQ_REQUIRE(out != nullptr, "out is NULL");
+    rrtqx_edges *e = new rrtqx_edges();
+    e->tree = tree;
+    *out = e;
+  });
+}
+
+rrtqx_status rrtqx_edges_destroy(rrtqx_edges *e) {
+  if (!e) return RRTQX_OK;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    delete e;
+  });
+}
+
+rrtqx_status rrtqx_edges_upload(rrtqx_edges *e, const int32_t *src, const int32_t *dst, int64_t n_edges,
+                                const int32_t *parent, int64_t n_parent) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(n_edges == 0 || (src && dst), "src / dst is NULL");
+    edges_upload(e, src, dst, n_edges, parent, n_parent);
+  });
+}
+
+rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges) {
+  if (!e || !n_edges) return RRTQX_ERR_INVALID;
+  *n_edges = e->n_edges;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_obstacle_add_sweep(rrtqx_edges *edges, const rrtqx_spheres *spheres, const int32_t *ob_ids,
+                                      int64_t n_obs, double robot_radius, double delta, uint32_t flags,
+                                      rrtqx_sweep_result **result) {
+  if (!edges || !spheres) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = edges->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(result != nullptr, "result is NULL");
+    RQ_REQUIRE(ob_ids != nullptr || n_obs == 0, "ob_ids is NULL");
+    if (!*result) *result = new rrtqx_sweep_result();
+    obstacle_add_sweep(edges, spheres, ob_ids, n_obs, robot_radius, delta, flags, *result);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_obstacle_remove_sweep(rrtqx_edges *edges, const rrtqx_spheres *spheres, int32_t ob_id,
+                                         const int32_t *other_ids, int64_t n_others, const uint8_t *edge_dist_inf,
+                                         double robot_radius, double delta, uint32_t flags,
+                                         rrtqx_sweep_result **result) {
+  if (!edges || !spheres) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = edges->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(result != nullptr, "result is NULL");
+    RQ_REQUIRE(other_ids != nullptr || n_others == 0, "other_ids is NULL");
+    if (!*result) *result = new rrtqx_sweep_result();
+    obstacle_remove_sweep(edges, spheres, ob_id, other_ids, n_others, edge_dist_inf, robot_radius, delta, flags, *result);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_sweep_result_destroy(rrtqx_sweep_result *r) {
+  if (!r) return RRTQX_OK;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    if (ctx) { bind_device(ctx); RQ_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    delete r;
+  });
+}
+
+rrtqx_status rrtqx_sweep_result_sizes(const rrtqx_sweep_result *r, int64_t *n_edge_hits, int64_t *n_node_hits,
+                                      int64_t *n_candidates, int64_t *n_pair_tests) {
+  if (!r) return RRTQX_ERR_INVALID;
+  if (n_edge_hits) *n_edge_hits = r->n_edge_hits;
+  if (n_node_hits) *n_node_hits = r->n_node_hits;
+  if (n_candidates) *n_candidates = r->n_candidates;
+  if (n_pair_tests) *n_pair_tests = r->n_pair_tests;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_sweep_result_fetch(rrtqx_sweep_result *r, int32_t *edge_ids, int32_t *node_ids) {
+  if (!r || !r->ctx) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    from_device(ctx, edge_ids, r->edge_list.p, (size_t)r->n_edge_hits);
+    from_device(ctx, node_ids, r->node_list.p, (size_t)r->n_node_hits);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_sweep_result_flags(rrtqx_sweep_result *r, uint8_t *edge_flag, uint8_t *node_flag) {
+  if (!r || !r->ctx) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = r->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    from_device(ctx, edge_flag, r->edge_flag.p, (size_t)r->n_edges);
+    from_device(ctx, node_flag, r->node_flag.p, (size_t)r->n_nodes);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// collision.cu -- batched explicitEdgeCheck / explicitPointCheck against the
+// sphere obstacle list (DRRT_Q.jl:1434-1595, 1775-1826).
+#include "objects.cuh"
+
+namespace rrtqx {
+
+// Active-obstacle table for one call: centre+radius, thr = robotRadius+radius,
+// thr_le = sqrt_thresh_le(thr).  Ordered compaction by a single block (the
+// obstacle list is small: tens to a few thousand entries).
+struct SphereTable {
+  const double4 *rec;   // (cx,cy,cz,R)
+  const double2 *thr;   // (thr, thr_le)
+  const int32_t *id;    // original obstacle index
+  int n;
+};
+
+__global__ void sphere_table_kernel(const double4 *__restrict__ rec, const uint8_t *__restrict__ active, int n,
+                                    int ignore_active, double robot_radius, double4 *__restrict__ out_rec,
+                                    double2 *__restrict__ out_thr, int32_t *__restrict__ out_id,
+                                    int32_t *__restrict__ out_n) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int b = 0; b < n; b += blockDim.x) {
+    int i = b + threadIdx.x;
+    bool keep = i < n && (ignore_active || active[i]);
+    unsigned m = __ballot_sync(FULL, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (keep) {
+      int o = off + __popc(m & lanemask_lt());
+      double4 r = rec[i];
+      double thr = __dadd_rn(robot_radius, r.w);  // robotRadius + thisObstacle.radius (DRRT_Q.jl:1790)
+      out_rec[o] = r;
+      out_thr[o] = make_double2(thr, sqrt_thresh_le(thr));
+      out_id[o] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += warp_cnt[w];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_n = base_s;
+}
+
+struct SphereTableBufs {
+  DevBuf<double4> rec;
+  DevBuf<double2> thr;
+  DevBuf<int32_t> id;
+  DevBuf<int32_t> n;
+};
+
+static SphereTableBufs &table_bufs(rrtqx_ctx *ctx) {
+  static std::map<rrtqx_ctx *, SphereTableBufs *> m;  // per context, leaked at exit by design
+  auto it = m.find(ctx);
+  if (it == m.end()) it = m.emplace(ctx, new SphereTableBufs()).first;
+  return *it->second;
+}
+
+// Builds the table on the stream; returns it with n = upper bound (all
+// obstacles) and writes the live count to *n_dev_out (device) for kernels.
+SphereTable build_sphere_table(rrtqx_ctx *ctx, const rrtqx_spheres *s, double robot_radius, uint32_t flags,
+                               const int32_t **n_dev_out) {
+  SphereTableBufs &b = table_bufs(ctx);
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)s->n;
+  b.rec.ensure(n + 1, st);
+  b.thr.ensure(n + 1, st);
+  b.id.ensure(n + 1, st);
+  b.n.ensure(4, st);
+  sphere_table_kernel<<<1, 1024, 0, st>>>(s->rec.p, s->active.p, (int)n, (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
+                                          robot_radius, b.rec.p, b.thr.p, b.id.p, b.n.p);
+  post_launch(ctx);
+  SphereTable t;
+  t.rec = b.rec.p;
+  t.thr = b.thr.p;
+  t.id = b.id.p;
+  t.n = (int)n;
+  *n_dev_out = b.n.p;
+  return t;
+}
+
+constexpr int SPH_TILE = 512;
+
+// One thread per edge; obstacle table staged through shared memory in tiles.
+// SRC_TREE: endpoints are gathered from the node table by index; otherwise
+// they are read from explicit start/end arrays (n x 3 row-major).
+template <bool FMA_DOT, bool SRC_TREE>
+__global__ void __launch_bounds__(256)
+edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                  const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
+                  SphereTable tab, const int32_t *__restrict__ n_live, uint8_t *__restrict__ out) {
+  __shared__ double4 s_rec[SPH_TILE];
+  __shared__ double2 s_thr[SPH_TILE];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_obs = *n_live;
+  SegPre pre;
+  bool valid = e < n_edges;
+  if (valid) {
+    if (SRC_TREE) {
+      double4 a = pos[src[e]], b = pos[dst[e]];
+      pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+    } else {
+      const double *a = starts + 3 * e, *b = ends + 3 * e;
+      pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
+    }
+  }
+  bool hit = false;
+  for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
+    const int tn = min(SPH_TILE, n_obs - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+      s_rec[k] = tab.rec[t0 + k];
+      s_thr[k] = tab.thr[t0 + k];
+    }
+    __syncthreads();
+    if (valid && !hit) {
+      for (int k = 0; k < tn; ++k) {
+        double4 o = s_rec[k];
+        double2 th = s_thr[k];
+        if (seg_sphere_collide<FMA_DOT>(pre, o.x, o.y, o.z, th.x, th.y)) { hit = true; break; }
+      }
+    }
+  }
+  if (valid) out[e] = hit ? 1 : 0;
+}
+
+void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                const int32_t *dst, const double *starts, const double *ends, int64_t n_edges, double robot_radius,
+                uint32_t flags, uint8_t *collide_out) {
+  if (n_edges <= 0) return;
+  cudaStream_t st = ctx->stream;
+  const bool from_tree = tree != nullptr;
+  const int32_t *dsrc = nullptr, *ddst = nullptr;
+  const double *dstarts = nullptr, *dends = nullptr;
+  if (from_tree) {
+    dsrc = to_device(ctx, src, (size_t)n_edges, ctx->stage_i32a);
+    ddst = to_device(ctx, dst, (size_t)n_edges, ctx->stage_i32b);
+  } else {
+    dstarts = to_device(ctx, starts, (size_t)n_edges * 3, ctx->stage_f64);
+    dends = to_device(ctx, ends, (size_t)n_edges * 3, ctx->stage_f64b);
+  }
+  const bool out_dev = is_device_ptr(collide_out);
+  uint8_t *dout = collide_out;
+  if (!out_dev) { ctx->stage_u8.ensure((size_t)n_edges, st); dout = ctx->stage_u8.p; }
+  {
+    PhaseScope ph(ctx, "edge_check");
+    const int32_t *n_live = nullptr;
+    SphereTable tab = build_sphere_table(ctx, spheres, robot_radius, flags, &n_live);
+    const int TB = 256;
+    const unsigned blocks = (unsigned)div_up(n_edges, TB);
+    const double4 *pos = from_tree ? tree->pos.p : nullptr;
+    const bool fma = flags & RRTQX_CHECK_FMA_DOT;
+    if (from_tree) {
+      if (fma) edge_check_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
+      else     edge_check_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
+    } else {
+      if (fma) edge_check_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
+      else     edge_check_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
+    }
+    post_launch(ctx);
+  }
+  if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n_edges);
+  RQ_CUDA(cudaStreamSynchronize(st));
+}
+
+// explicitPointCheck (DRRT_Q.jl:1520-1556) / explicitPointCheck3D (:1558-1590),
+// one thread per point, literal sequential semantics over the active list.
+template <bool QUICK>
+__global__ void __launch_bounds__(256)
+node_check_kernel(const double *__restrict__ pts, int64_t n, SphereTable tab, const int32_t *__restrict__ n_live,
+                  double robot_radius, uint8_t *__restrict__ out, double *__restrict__ cert_out) {
+  __shared__ double4 s_rec[SPH_TILE];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_obs = *n_live;
+  const bool valid = i < n;
+  double p[3] = {0, 0, 0};
+  if (valid) { p[0] = pts[3 * i]; p[1] = pts[3 * i + 1]; p[2] = pts[3 * i + 2]; }
+  bool hit = false;
+  if (QUICK) {  // quickCheck :1434-1452 -> quickCheck2D :1402-1415
+    for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
+      const int tn = min(SPH_TILE, n_obs - t0);
+      __syncthreads();
+      for (int k = threadIdx.x; k < tn; k += blockDim.x) s_rec[k] = tab.rec[t0 + k];
+      __syncthreads();
+      if (valid && !hit)
+        for (int k = 0; k < tn; ++k) {
+          double4 o = s_rec[k];
+          double c[3] = {o.x, o.y, o.z};
+          double dd = __dsqrt_rn(sqdist<3>(c, p[0], p[1], p[2], 0.0));
+          if (!(dd > o.w)) { hit = true; break; }
+        }
+    }
+  }
+  double ret_cert = INFINITY;
+  for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
+    const int tn = min(SPH_TILE, n_obs - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) s_rec[k] = tab.rec[t0 + k];
+    __syncthreads();
+    if (valid && !hit)
+      for (int k = 0; k < tn; ++k) {  // explicitPointCheck2D :1463-1487
+        double4 o = s_rec[k];
+        double c[3] = {o.x, o.y, o.z};
+        double this_dist = __dsub_rn(__dsqrt_rn(sqdist<3>(c, p[0], p[1], p[2], 0.0)), robot_radius);
+        if (__dsub_rn(this_dist, o.w) > ret_cert) continue;
+        this_dist = __dsub_rn(this_dist, o.w);
+        if (this_dist < 0.0) { hit = true; break; }
+        double this_cert = jl_min(ret_cert, this_dist);
+        if (this_cert < ret_cert) ret_cert = this_cert;  // :1545-1547
+      }
+  }
+  if (valid) {
+    out[i] = hit ? 1 : 0;
+    if (cert_out) cert_out[i] = hit ? 0.0 : ret_cert;
+  }
+}
+
+void node_check(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *points, int64_t n, double robot_radius,
+                uint32_t flags, uint8_t *collide_out, double *cert_out) {
+  if (n <= 0) return;
+  cudaStream_t st = ctx->stream;
+  const double *dp = to_device(ctx, points, (size_t)n * 3, ctx->stage_f64);
+  const bool out_dev = is_device_ptr(collide_out), cert_dev = cert_out && is_device_ptr(cert_out);
+  uint8_t *dout = collide_out;
+  double *dcert = cert_out;
+  if (!out_dev) { ctx->stage_u8.ensure((size_t)n, st); dout = ctx->stage_u8.p; }
+  if (cert_out && !cert_dev) { ctx->stage_f64b.ensure((size_t)n, st); dcert = ctx->stage_f64b.p; }
+  {
+    PhaseScope ph(ctx, "node_check");
+    const int32_t *n_live = nullptr;
+    SphereTable tab = build_sphere_table(ctx, spheres, robot_radius, flags, &n_live);
+    const int TB = 256;
+    const unsigned blocks = (unsigned)div_up(n, TB);
+    if (flags & RRTQX_CHECK_QUICK_PASS)
+      node_check_kernel<true><<<blocks, TB, 0, st>>>(dp, n, tab, n_live, robot_radius, dout, dcert);
+    else
+      node_check_kernel<false><<<blocks, TB, 0, st>>>(dp, n, tab, n_live, robot_radius, dout, dcert);
+    post_launch(ctx);
+  }
+  if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n);
+  if (cert_out && !cert_dev) from_device(ctx, cert_out, dcert, (size_t)n);
+  RQ_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace rrtqx

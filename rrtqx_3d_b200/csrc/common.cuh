@@ -1,0 +1,254 @@
+// common.cuh -- shared host/device infrastructure of librrtqx_b200.so.
+// sm_100a only; compiled with -fmad=false, and every arithmetic step that
+// decides a result uses the explicit round-to-nearest intrinsics so that no
+// FMA contraction can ever change a bit.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rrtqx_b200.h"
+
+namespace rrtqx {
+
+// ------------------------------------------------------------------ errors
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define RQ_CUDA(expr)                                                         \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      char _b[512];                                                           \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr,                \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+      throw ::rrtqx::Error(_e == cudaErrorMemoryAllocation ? RRTQX_ERR_NOMEM  \
+                                                           : RRTQX_ERR_CUDA,  \
+                           _b);                                               \
+    }                                                                         \
+  } while (0)
+
+#define RQ_REQUIRE(cond, msg)                                                 \
+  do {                                                                        \
+    if (!(cond)) throw ::rrtqx::Error(RRTQX_ERR_INVALID, msg);                \
+  } while (0)
+
+// --------------------------------------------------------- device buffers
+// Grow-only typed device buffer.  Frees are deferred to destruction so that
+// work already queued on the stream never loses its memory.
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  std::vector<T *> graveyard;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    for (T *g : graveyard) cudaFree(g);
+    graveyard.clear();
+    p = nullptr;
+    cap = 0;
+  }
+  // Ensure capacity >= n elements.  preserve = number of leading elements to
+  // keep (copied on `stream`).
+  void ensure(size_t n, cudaStream_t stream = 0, size_t preserve = 0,
+              double growth = 1.5) {
+    if (n <= cap) return;
+    size_t nc = (size_t)((double)cap * growth);
+    if (nc < n) nc = n;
+    if (nc < 256) nc = 256;
+    T *np = nullptr;
+    RQ_CUDA(cudaMalloc((void **)&np, nc * sizeof(T)));
+    if (p && preserve) {
+      RQ_CUDA(cudaMemcpyAsync(np, p, preserve * sizeof(T),
+                              cudaMemcpyDeviceToDevice, stream));
+    }
+    if (p) graveyard.push_back(p);
+    p = np;
+    cap = nc;
+  }
+  // Free retired allocations; only call after the stream has been synchronised.
+  void collect() {
+    for (T *g : graveyard) cudaFree(g);
+    graveyard.clear();
+  }
+};
+
+inline bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace rrtqx
+
+// ------------------------------------------------------------------ context
+struct rrtqx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  struct Phase {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool valid = false;
+  };
+  std::map<std::string, Phase> phases;
+  // staging buffers for host<->device traffic of the batched calls
+  rrtqx::DevBuf<double> stage_f64;
+  rrtqx::DevBuf<int32_t> stage_i32a, stage_i32b;
+  rrtqx::DevBuf<uint8_t> stage_u8;
+  rrtqx::DevBuf<double> stage_f64b;
+
+  void phase_begin(const char *name) {
+    Phase &p = phases[name];
+    if (!p.a) {
+      cudaEventCreate(&p.a);
+      cudaEventCreate(&p.b);
+    }
+    cudaEventRecord(p.a, stream);
+    p.valid = false;
+  }
+  void phase_end(const char *name) {
+    Phase &p = phases[name];
+    cudaEventRecord(p.b, stream);
+    p.valid = true;
+  }
+};
+
+namespace rrtqx {
+
+// RAII phase timer
+struct PhaseScope {
+  rrtqx_ctx *c;
+  const char *n;
+  PhaseScope(rrtqx_ctx *c_, const char *n_) : c(c_), n(n_) { c->phase_begin(n); }
+  ~PhaseScope() { c->phase_end(n); }
+};
+
+inline void post_launch(rrtqx_ctx *ctx, int n = 1) {
+  ctx->launches += n;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw Error(RRTQX_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// Input array that may live on host or device: returns a device pointer valid
+// on ctx->stream, staging through `buf` when the source is host memory.
+template <typename T>
+const T *to_device(rrtqx_ctx *ctx, const T *src, size_t n, DevBuf<T> &buf) {
+  if (n == 0 || src == nullptr) return nullptr;
+  if (is_device_ptr(src)) return src;
+  buf.ensure(n, ctx->stream);
+  RQ_CUDA(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return buf.p;
+}
+
+// Copy n elements from device memory to a host-or-device destination.
+template <typename T>
+void from_device(rrtqx_ctx *ctx, T *dst, const T *src_dev, size_t n) {
+  if (n == 0 || dst == nullptr) return;
+  RQ_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(T), cudaMemcpyDefault, ctx->stream));
+}
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------ device math
+#ifdef __CUDACC__
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// euclidianDist radicand (DRRT_distance_functions.jl:37): left-to-right sum of
+// individually rounded squares of individually rounded differences.
+template <int D>
+__device__ __forceinline__ double sqdist(const double *q, double px, double py, double pz, double pw) {
+  double dx = __dsub_rn(q[0], px);
+  double dy = __dsub_rn(q[1], py);
+  double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  if (D >= 3) {
+    double dz = __dsub_rn(q[2], pz);
+    s = __dadd_rn(s, __dmul_rn(dz, dz));
+  }
+  if (D >= 4) {
+    double dw = __dsub_rn(q[3], pw);
+    s = __dadd_rn(s, __dmul_rn(dw, dw));
+  }
+  return s;
+}
+
+__device__ __forceinline__ double next_up(double x) {  // x finite, >= 0
+  return __longlong_as_double(__double_as_longlong(x) + 1);
+}
+__device__ __forceinline__ double next_down(double x) {  // x finite, > 0
+  return __longlong_as_double(__double_as_longlong(x) - 1);
+}
+
+// T_lt(r) = min{ t >= 0 : fl(sqrt(t)) >= r }  so that  sqrt(s) < r  <=>  s < T_lt
+// (monotonicity of correctly rounded sqrt).
+__device__ inline double sqrt_thresh_lt(double r) {
+  if (r != r) return r;            // NaN: s < NaN is false for every s
+  if (r <= 0.0) return 0.0;        // sqrt(s) < r never holds
+  if (isinf(r)) return r;          // every finite s qualifies
+  double t = __dmul_rn(r, r);
+  if (isinf(t)) {                  // r^2 overflows: search below DBL_MAX
+    t = 1.7976931348623157e308;
+    if (__dsqrt_rn(t) < r) return __longlong_as_double(0x7ff0000000000000LL);
+  }
+  while (t > 0.0 && __dsqrt_rn(t) >= r) t = next_down(t);
+  while (__dsqrt_rn(t) < r) t = next_up(t);
+  return t;
+}
+
+// T_le(r) = max{ t : fl(sqrt(t)) <= r }  so that  sqrt(s) <= r <=> s <= T_le
+// and  sqrt(s) > r <=> s > T_le.   Returns -1 if no t >= 0 qualifies.
+__device__ inline double sqrt_thresh_le(double r) {
+  if (r != r) return r;            // comparisons with NaN are false
+  if (r < 0.0) return -1.0;
+  if (isinf(r)) return r;
+  double t = __dmul_rn(r, r);
+  if (isinf(t)) t = 1.7976931348623157e308;
+  while (__dsqrt_rn(t) <= r && t < 1.7976931348623157e308) t = next_up(t);
+  while (t > 0.0 && __dsqrt_rn(t) > r) t = next_down(t);
+  return t;
+}
+
+// Julia Base.min / Base.max on Float64: NaN-propagating, -0.0 < +0.0.
+__device__ __forceinline__ double jl_min(double x, double y) {
+  bool sy = __double_as_longlong(y) < 0, sx = __double_as_longlong(x) < 0;
+  if ((y < x) || (sy && !sx)) return (x != x) ? x : y;
+  return (y != y) ? y : x;
+}
+__device__ __forceinline__ double jl_max(double x, double y) {
+  bool sy = __double_as_longlong(y) < 0, sx = __double_as_longlong(x) < 0;
+  if ((y > x) || (!sy && sx)) return (x != x) ? x : y;
+  return (y != y) ? y : x;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rrtqx

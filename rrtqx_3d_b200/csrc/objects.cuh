@@ -1,0 +1,72 @@
+// objects.cuh -- handle types behind the C ABI and the internal entry points
+// each translation unit provides.
+#pragma once
+#include "collision.cuh"
+#include "common.cuh"
+#include "tree.cuh"
+
+struct rrtqx_range_result {
+  rrtqx_ctx *ctx = nullptr;
+  int64_t n_queries = 0;
+  int64_t total = 0;
+  bool has_dist = false;
+  bool has_lists = false;
+  rrtqx::DevBuf<int32_t> counts;
+  rrtqx::DevBuf<int64_t> offsets;
+  rrtqx::DevBuf<int32_t> idx;
+  rrtqx::DevBuf<double> dist;
+  // query sort scratch
+  rrtqx::DevBuf<int32_t> qkey, qorder, qhist, qstart;
+  rrtqx::DevBuf<int32_t> scan_tmp32;
+  rrtqx::DevBuf<int64_t> scan_tmp64;
+};
+
+struct rrtqx_edges {
+  rrtqx_tree *tree = nullptr;
+  int64_t n_edges = 0;
+  int64_t n_nodes = 0;  // tree size at upload
+  bool has_parent = false;
+  rrtqx::DevBuf<int32_t> src, dst;            // upload order (edge id = position)
+  rrtqx::DevBuf<int32_t> row_ptr, cursor;     // CSR by start node
+  rrtqx::DevBuf<int32_t> csr_dst, csr_eid;
+  rrtqx::DevBuf<int32_t> parent;
+  rrtqx::DevBuf<double> lmax;                 // per node: longest out/parent edge (cull bound)
+  rrtqx::DevBuf<uint8_t> degenerate;          // per node: some edge has len == 0 or non-finite ends
+  rrtqx::DevBuf<int32_t> scan_tmp;
+};
+
+struct rrtqx_sweep_result {
+  rrtqx_ctx *ctx = nullptr;
+  int64_t n_edges = 0, n_nodes = 0;
+  int64_t n_edge_hits = 0, n_node_hits = 0, n_candidates = 0, n_pair_tests = 0;
+  rrtqx::DevBuf<uint8_t> edge_flag, node_flag;
+  rrtqx::DevBuf<int32_t> edge_scan, node_scan, edge_list, node_list, scan_tmp;
+  rrtqx::DevBuf<unsigned long long> stats;
+  // obstacle table of the sweep
+  rrtqx::DevBuf<double4> ob_rec;
+  rrtqx::DevBuf<double4> ob_par;  // (thr, thr_le, search_T_lt, search_range)
+  rrtqx::DevBuf<int32_t> ids_stage, ids_stage2;
+  rrtqx::DevBuf<uint8_t> inf_stage;
+};
+
+namespace rrtqx {
+// range.cu
+void range_query(rrtqx_tree *t, const double *queries, int64_t nq, double r, const double *ranges, uint32_t flags,
+                 rrtqx_range_result *res);
+void nearest_query(rrtqx_tree *t, rrtqx_range_result *sortbuf, const double *queries, int64_t nq, int32_t *idx_out,
+                   double *dist_out, DevBuf<int32_t> &idx_stage, DevBuf<double> &dist_stage);
+// collision.cu
+void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                const int32_t *dst, const double *starts, const double *ends, int64_t n_edges, double robot_radius,
+                uint32_t flags, uint8_t *collide_out);
+void node_check(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *points, int64_t n, double robot_radius,
+                uint32_t flags, uint8_t *collide_out, double *cert_out);
+// sweep.cu
+void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
+                  int64_t n_parent);
+void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *ob_ids, int64_t n_obs,
+                        double robot_radius, double delta, uint32_t flags, rrtqx_sweep_result *R);
+void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id, const int32_t *other_ids,
+                           int64_t n_others, const uint8_t *edge_dist_inf, double robot_radius, double delta,
+                           uint32_t flags, rrtqx_sweep_result *R);
+}  // namespace rrtqx

@@ -1,0 +1,399 @@
+// sweep.cu -- resident out-edge lists and the obstacle add / remove sweeps
+// (addNewObstacle DRRT_Q.jl:3220-3290, removeObstacle :3295-3362,
+// findPointsInConflictWithObstacle :3195-3215).
+//
+// Only the geometric decisions are made here; the Julia side applies the list
+// surgery (edge.dist = Inf, orphaning, queue pushes) to the returned id sets.
+#include "objects.cuh"
+#include "scan.cuh"
+
+namespace rrtqx {
+
+// ------------------------------------------------------------ CSR build
+__global__ void edge_hist_kernel(const int32_t *__restrict__ src, int64_t ne, int32_t *__restrict__ cnt) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ne) atomicAdd(&cnt[src[e]], 1);
+}
+__global__ void edge_scatter_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t ne,
+                                    const int32_t *__restrict__ row_ptr, int32_t *__restrict__ cursor,
+                                    int32_t *__restrict__ csr_eid) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int v = src[e];
+  csr_eid[row_ptr[v] + atomicAdd(&cursor[v], 1)] = (int32_t)e;
+}
+// per row: ascending edge id (deterministic), then dst and the node's cull data
+__global__ void edge_rows_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ dst,
+                                 const int32_t *__restrict__ row_ptr, int32_t *__restrict__ csr_eid,
+                                 int32_t *__restrict__ csr_dst, const int32_t *__restrict__ parent, int64_t n_nodes,
+                                 double *__restrict__ lmax, uint8_t *__restrict__ degenerate) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_nodes) return;
+  int a = row_ptr[v], b = row_ptr[v + 1];
+  if (b - a <= 256)
+    for (int i = a + 1; i < b; ++i) {
+      int x = csr_eid[i];
+      int j = i - 1;
+      while (j >= a && csr_eid[j] > x) { csr_eid[j + 1] = csr_eid[j]; --j; }
+      csr_eid[j + 1] = x;
+    }
+  double4 p = pos[v];
+  double lm = 0.0;
+  bool degen = false;
+  for (int i = a; i < b; ++i) {
+    int w = dst[csr_eid[i]];
+    csr_dst[i] = w;
+    double4 q = pos[w];
+    SegPre s = seg_prepare(p.x, p.y, p.z, q.x, q.y, q.z);
+    if (!s.cullable) degen = true; else lm = fmax(lm, s.len);
+  }
+  if (parent && parent[v] >= 0) {
+    double4 q = pos[parent[v]];
+    SegPre s = seg_prepare(p.x, p.y, p.z, q.x, q.y, q.z);
+    if (!s.cullable) degen = true; else lm = fmax(lm, s.len);
+  }
+  lmax[v] = lm;
+  degenerate[v] = degen ? 1 : 0;
+}
+
+void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
+                  int64_t n_parent) {
+  rrtqx_tree *t = E->tree;
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
+  RQ_REQUIRE(ne >= 0 && ne < (int64_t)0x7fffffff, "n_edges out of range");
+  const int64_t nn = t->n;
+  RQ_REQUIRE(parent == nullptr || n_parent == nn, "parent array must have one entry per tree node");
+  E->n_edges = ne;
+  E->n_nodes = nn;
+  E->has_parent = parent != nullptr;
+  E->src.ensure((size_t)ne + 1, st);
+  E->dst.ensure((size_t)ne + 1, st);
+  E->csr_dst.ensure((size_t)ne + 1, st);
+  E->csr_eid.ensure((size_t)ne + 1, st);
+  E->row_ptr.ensure((size_t)nn + 2, st);
+  E->cursor.ensure((size_t)nn + 2, st);
+  E->parent.ensure((size_t)nn + 1, st);
+  E->lmax.ensure((size_t)nn + 1, st);
+  E->degenerate.ensure((size_t)nn + 1, st);
+  if (ne) {
+    RQ_CUDA(cudaMemcpyAsync(E->src.p, src, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
+    RQ_CUDA(cudaMemcpyAsync(E->dst.p, dst, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
+  }
+  if (parent) RQ_CUDA(cudaMemcpyAsync(E->parent.p, parent, sizeof(int32_t) * nn, cudaMemcpyDefault, st));
+  // validate indices on the host side only when the arrays are host arrays
+  if (ne && !is_device_ptr(src)) {
+    for (int64_t e = 0; e < ne; ++e)
+      RQ_REQUIRE(src[e] >= 0 && src[e] < nn && dst[e] >= 0 && dst[e] < nn, "edge endpoint out of range");
+  }
+  const int TB = 256;
+  RQ_CUDA(cudaMemsetAsync(E->cursor.p, 0, sizeof(int32_t) * ((size_t)nn + 1), st));
+  if (ne) { edge_hist_kernel<<<div_up(ne, TB), TB, 0, st>>>(E->src.p, ne, E->cursor.p); post_launch(ctx); }
+  exclusive_scan<int32_t, int32_t>(ctx, E->cursor.p, nn, E->row_ptr.p, E->scan_tmp);
+  RQ_CUDA(cudaMemsetAsync(E->cursor.p, 0, sizeof(int32_t) * ((size_t)nn + 1), st));
+  if (ne) {
+    edge_scatter_kernel<<<div_up(ne, TB), TB, 0, st>>>(E->src.p, E->dst.p, ne, E->row_ptr.p, E->cursor.p, E->csr_eid.p);
+    post_launch(ctx);
+  }
+  if (nn) {
+    edge_rows_kernel<<<div_up(nn, TB), TB, 0, st>>>(t->pos.p, E->dst.p, E->row_ptr.p, E->csr_eid.p, E->csr_dst.p,
+                                                    parent ? E->parent.p : nullptr, nn, E->lmax.p, E->degenerate.p);
+    post_launch(ctx);
+  }
+  RQ_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------ sweep obstacle table
+__global__ void sweep_table_kernel(const double4 *__restrict__ rec, const int32_t *__restrict__ ids, int n,
+                                   double robot_radius, double delta, double4 *__restrict__ out_rec,
+                                   double4 *__restrict__ out_par) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 r = rec[ids[i]];
+  double thr = __dadd_rn(robot_radius, r.w);                       // DRRT_Q.jl:1790
+  double sr = __dadd_rn(__dadd_rn(robot_radius, delta), r.w);     // :3203 searchRange, left to right
+  out_rec[i] = r;
+  out_par[i] = make_double4(thr, sqrt_thresh_le(thr), sqrt_thresh_lt(sr), sr);
+}
+
+constexpr int SW_TILE = 256;  // obstacles per shared-memory tile
+
+// addNewObstacle: one warp per node.  Lanes first sweep the obstacle tile
+// (candidate = start-node filter, then a conservative bound using the node's
+// longest edge); surviving obstacles are processed cooperatively, lanes over
+// the node's out-edges + parent edge with the exact predicate.
+template <bool FMA_DOT>
+__global__ void __launch_bounds__(256)
+add_sweep_kernel(const double4 *__restrict__ pos, int n_nodes, const int32_t *__restrict__ row_ptr,
+                 const int32_t *__restrict__ csr_dst, const int32_t *__restrict__ csr_eid,
+                 const int32_t *__restrict__ parent, const double *__restrict__ lmax,
+                 const uint8_t *__restrict__ degenerate, const double4 *__restrict__ ob_rec,
+                 const double4 *__restrict__ ob_par, int n_obs, uint8_t *__restrict__ edge_flag,
+                 uint8_t *__restrict__ node_flag, unsigned long long *__restrict__ stats) {
+  __shared__ double4 s_rec[SW_TILE];
+  __shared__ double4 s_par[SW_TILE];
+  __shared__ unsigned long long s_stats[2];
+  const int lane = lane_id();
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long ncand = 0, ntests = 0;
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+
+  for (int t0 = 0; t0 < n_obs; t0 += SW_TILE) {
+    const int tn = min(SW_TILE, n_obs - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) { s_rec[k] = ob_rec[t0 + k]; s_par[k] = ob_par[t0 + k]; }
+    __syncthreads();
+    for (int v = warp0; v < n_nodes; v += nwarps) {
+      const double4 p = pos[v];
+      const int ra = row_ptr[v], rb = row_ptr[v + 1];
+      const int par = parent ? parent[v] : -1;
+      const int deg = (rb - ra) + (par >= 0 ? 1 : 0);
+      const double lm = lmax[v];
+      const bool degen = degenerate[v] != 0;
+      // lane's first edge, prepared lazily
+      SegPre pre;
+      bool have_pre = false;
+      for (int o0 = 0; o0 < tn; o0 += 32) {
+        const int o = o0 + lane;
+        bool need = false;
+        if (o < tn) {
+          const double4 c = s_rec[o];
+          const double4 pr = s_par[o];
+          const double q[3] = {c.x, c.y, c.z};
+          const double s = sqdist<3>(q, p.x, p.y, p.z, 0.0);  // euclid(ob.position, node.position)
+          bool cand = s < pr.z;                                 // < searchRange
+          if (!cand && v == 0) cand = __dsqrt_rn(s) <= pr.w;    // root admitted with <= (kdTree_general.jl:896)
+          if (cand) {
+            ncand += 1;
+            ntests += (unsigned long long)deg;
+            if (deg > 0) {
+              const double lim = (pr.x + lm) * (1.0 + 1e-9);
+              need = degen || !(s > lim * lim) || !isfinite(lim);
+            }
+          }
+        }
+        unsigned m = __ballot_sync(FULL, need);
+        while (m) {
+          const int ol = __ffs(m) - 1;
+          m &= m - 1;
+          const double4 c = s_rec[o0 + ol];
+          const double4 pr = s_par[o0 + ol];
+          for (int k0 = 0; k0 < deg; k0 += 32) {
+            const int k = k0 + lane;
+            if (k < deg) {
+              const bool is_parent = k >= (rb - ra);
+              const int w = is_parent ? par : csr_dst[ra + k];
+              SegPre cur;
+              if (k0 == 0 && have_pre) {
+                cur = pre;
+              } else {
+                const double4 e = pos[w];
+                cur = seg_prepare(p.x, p.y, p.z, e.x, e.y, e.z);
+                if (k0 == 0) { pre = cur; have_pre = true; }
+              }
+              if (seg_sphere_collide<FMA_DOT>(cur, c.x, c.y, c.z, pr.x, pr.y)) {
+                if (is_parent) node_flag[v] = 1;          // :3257-3270 orphan
+                else edge_flag[csr_eid[ra + k]] = 1;      // :3248-3249 edge.dist = Inf
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // block-aggregated statistics: one global atomic pair per block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ncand += __shfl_xor_sync(FULL, ncand, o);
+    ntests += __shfl_xor_sync(FULL, ntests, o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    atomicAdd(&s_stats[0], ncand);
+    atomicAdd(&s_stats[1], ntests);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// removeObstacle: one thread per edge (upload order).  ob = table entry 0,
+// others = entries 1..n_tab-1 (thr / thr_le only).
+template <bool FMA_DOT>
+__global__ void __launch_bounds__(256)
+remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                    int64_t n_edges, const uint8_t *__restrict__ edge_dist_inf, const double4 *__restrict__ ob_rec,
+                    const double4 *__restrict__ ob_par, int n_tab, int removed_inactive,
+                    uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag,
+                    unsigned long long *__restrict__ stats) {
+  __shared__ double4 s_rec[SW_TILE];
+  __shared__ double4 s_par[SW_TILE];
+  __shared__ unsigned s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e < n_edges;
+  const double4 c0 = ob_rec[0];
+  const double4 p0 = ob_par[0];
+  bool pending = false;  // flagged edge that collides with the removed obstacle
+  SegPre pre;
+  int v = 0;
+  if (valid) {
+    v = src[e];
+    const double4 p = pos[v];
+    const double q[3] = {c0.x, c0.y, c0.z};
+    const double s = sqdist<3>(q, p.x, p.y, p.z, 0.0);
+    bool cand = s < p0.z;
+    if (!cand && v == 0) cand = __dsqrt_rn(s) <= p0.w;
+    if (cand) {
+      atomicAdd(&s_cnt, 1u);  // (edge, obstacle) pairs that pass the start-node filter
+      if (edge_dist_inf[e] && !removed_inactive) {  // DRRT_Q.jl:3319 (QX: obstacle already unused -> false)
+        const double4 w = pos[dst[e]];
+        pre = seg_prepare(p.x, p.y, p.z, w.x, w.y, w.z);
+        pending = seg_sphere_collide<FMA_DOT>(pre, c0.x, c0.y, c0.z, p0.x, p0.y);
+      }
+    }
+  }
+  bool conflicts = false;
+  for (int t0 = 1; t0 < n_tab; t0 += SW_TILE) {  // :3326-3337 every other active obstacle
+    const int tn = min(SW_TILE, n_tab - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) { s_rec[k] = ob_rec[t0 + k]; s_par[k] = ob_par[t0 + k]; }
+    __syncthreads();
+    if (pending && !conflicts)
+      for (int k = 0; k < tn; ++k)
+        if (seg_sphere_collide<FMA_DOT>(pre, s_rec[k].x, s_rec[k].y, s_rec[k].z, s_par[k].x, s_par[k].y)) {
+          conflicts = true;
+          break;
+        }
+  }
+  if (pending && !conflicts) {  // :3340-3346
+    edge_flag[e] = 1;
+    node_flag[v] = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(&stats[1], (unsigned long long)s_cnt);
+}
+
+// ------------------------------------------------------- flag compaction
+__global__ void compact_flags_kernel(const uint8_t *__restrict__ flag, const int32_t *__restrict__ scan, int64_t n,
+                                     int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[scan[i]] = (int32_t)i;
+}
+
+static void finish_sweep(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
+  cudaStream_t st = ctx->stream;
+  const int TB = 256;
+  R->edge_scan.ensure((size_t)R->n_edges + 2, st);
+  R->node_scan.ensure((size_t)R->n_nodes + 2, st);
+  exclusive_scan<uint8_t, int32_t>(ctx, R->edge_flag.p, R->n_edges, R->edge_scan.p, R->scan_tmp);
+  exclusive_scan<uint8_t, int32_t>(ctx, R->node_flag.p, R->n_nodes, R->node_scan.p, R->scan_tmp);
+  int32_t ne_hits = 0, nn_hits = 0;
+  unsigned long long stats[2] = {0, 0};
+  RQ_CUDA(cudaMemcpyAsync(&ne_hits, R->edge_scan.p + R->n_edges, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaMemcpyAsync(&nn_hits, R->node_scan.p + R->n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaMemcpyAsync(stats, R->stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaStreamSynchronize(st));
+  R->n_edge_hits = ne_hits;
+  R->n_node_hits = nn_hits;
+  R->n_candidates = (int64_t)stats[0];
+  R->n_pair_tests = (int64_t)stats[1];
+  R->edge_list.ensure((size_t)ne_hits + 1, st);
+  R->node_list.ensure((size_t)nn_hits + 1, st);
+  if (R->n_edges) compact_flags_kernel<<<div_up(R->n_edges, TB), TB, 0, st>>>(R->edge_flag.p, R->edge_scan.p, R->n_edges, R->edge_list.p);
+  if (R->n_nodes) compact_flags_kernel<<<div_up(R->n_nodes, TB), TB, 0, st>>>(R->node_flag.p, R->node_scan.p, R->n_nodes, R->node_list.p);
+  post_launch(ctx, 2);
+}
+
+static void prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
+  rrtqx_ctx *ctx = E->tree->ctx;
+  cudaStream_t st = ctx->stream;
+  R->ctx = ctx;
+  R->n_edges = E->n_edges;
+  R->n_nodes = E->n_nodes;
+  R->edge_flag.ensure((size_t)E->n_edges + 1, st);
+  R->node_flag.ensure((size_t)E->n_nodes + 1, st);
+  R->stats.ensure(4, st);
+  RQ_CUDA(cudaMemsetAsync(R->edge_flag.p, 0, (size_t)E->n_edges + 1, st));
+  RQ_CUDA(cudaMemsetAsync(R->node_flag.p, 0, (size_t)E->n_nodes + 1, st));
+  RQ_CUDA(cudaMemsetAsync(R->stats.p, 0, 4 * sizeof(unsigned long long), st));
+}
+
+void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *ob_ids, int64_t n_obs,
+                        double robot_radius, double delta, uint32_t flags, rrtqx_sweep_result *R) {
+  rrtqx_ctx *ctx = E->tree->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(n_obs >= 0 && n_obs < (1 << 24), "n_obs out of range");
+  if (!is_device_ptr(ob_ids))
+    for (int64_t i = 0; i < n_obs; ++i) RQ_REQUIRE(ob_ids[i] >= 0 && ob_ids[i] < S->n, "obstacle id out of range");
+  const int32_t *dids = to_device(ctx, ob_ids, (size_t)n_obs, R->ids_stage);
+  PhaseScope ph(ctx, "add_sweep");
+  prepare_result(E, R);
+  if (n_obs > 0 && E->n_nodes > 0) {
+    R->ob_rec.ensure((size_t)n_obs, st);
+    R->ob_par.ensure((size_t)n_obs, st);
+    const int TB = 256;
+    sweep_table_kernel<<<div_up(n_obs, TB), TB, 0, st>>>(S->rec.p, dids, (int)n_obs, robot_radius, delta, R->ob_rec.p, R->ob_par.p);
+    const int blocks = std::max(1, std::min(div_up(E->n_nodes * 32, TB), ctx->sm_count * 8));
+    const int32_t *par = E->has_parent ? E->parent.p : nullptr;
+    if (flags & RRTQX_CHECK_FMA_DOT)
+      add_sweep_kernel<true><<<blocks, TB, 0, st>>>(E->tree->pos.p, (int)E->n_nodes, E->row_ptr.p, E->csr_dst.p, E->csr_eid.p, par,
+                                                    E->lmax.p, E->degenerate.p, R->ob_rec.p, R->ob_par.p, (int)n_obs,
+                                                    R->edge_flag.p, R->node_flag.p, R->stats.p);
+    else
+      add_sweep_kernel<false><<<blocks, TB, 0, st>>>(E->tree->pos.p, (int)E->n_nodes, E->row_ptr.p, E->csr_dst.p, E->csr_eid.p, par,
+                                                     E->lmax.p, E->degenerate.p, R->ob_rec.p, R->ob_par.p, (int)n_obs,
+                                                     R->edge_flag.p, R->node_flag.p, R->stats.p);
+    post_launch(ctx, 2);
+  }
+  finish_sweep(ctx, R);
+}
+
+void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id, const int32_t *other_ids,
+                           int64_t n_others, const uint8_t *edge_dist_inf, double robot_radius, double delta,
+                           uint32_t flags, rrtqx_sweep_result *R) {
+  rrtqx_ctx *ctx = E->tree->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(ob_id >= 0 && ob_id < S->n, "obstacle id out of range");
+  RQ_REQUIRE(n_others >= 0 && n_others < (1 << 24), "n_others out of range");
+  RQ_REQUIRE(edge_dist_inf != nullptr || E->n_edges == 0, "edge_dist_inf is NULL");
+  // table = [ob_id, others...]
+  std::vector<int32_t> ids((size_t)n_others + 1);
+  ids[0] = ob_id;
+  if (n_others) {
+    if (is_device_ptr(other_ids))
+      RQ_CUDA(cudaMemcpy(ids.data() + 1, other_ids, sizeof(int32_t) * n_others, cudaMemcpyDeviceToHost));
+    else
+      memcpy(ids.data() + 1, other_ids, sizeof(int32_t) * n_others);
+  }
+  for (size_t i = 0; i < ids.size(); ++i) RQ_REQUIRE(ids[i] >= 0 && ids[i] < S->n, "obstacle id out of range");
+  R->ids_stage2.ensure(ids.size(), st);
+  RQ_CUDA(cudaMemcpyAsync(R->ids_stage2.p, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, st));
+  RQ_CUDA(cudaStreamSynchronize(st));  // ids is a local vector
+  const uint8_t *dinf = to_device(ctx, edge_dist_inf, (size_t)E->n_edges, R->inf_stage);
+  PhaseScope ph(ctx, "remove_sweep");
+  prepare_result(E, R);
+  const int n_tab = (int)ids.size();
+  R->ob_rec.ensure((size_t)n_tab, st);
+  R->ob_par.ensure((size_t)n_tab, st);
+  const int TB = 256;
+  sweep_table_kernel<<<div_up(n_tab, TB), TB, 0, st>>>(S->rec.p, R->ids_stage2.p, n_tab, robot_radius, delta, R->ob_rec.p, R->ob_par.p);
+  post_launch(ctx);
+  if (E->n_edges > 0) {
+    const int removed_inactive = (flags & RRTQX_SWEEP_REMOVED_INACTIVE) ? 1 : 0;
+    if (flags & RRTQX_CHECK_FMA_DOT)
+      remove_sweep_kernel<true><<<div_up(E->n_edges, TB), TB, 0, st>>>(E->tree->pos.p, E->src.p, E->dst.p, E->n_edges, dinf, R->ob_rec.p,
+                                                                      R->ob_par.p, n_tab, removed_inactive, R->edge_flag.p,
+                                                                      R->node_flag.p, R->stats.p);
+    else
+      remove_sweep_kernel<false><<<div_up(E->n_edges, TB), TB, 0, st>>>(E->tree->pos.p, E->src.p, E->dst.p, E->n_edges, dinf, R->ob_rec.p,
+                                                                       R->ob_par.p, n_tab, removed_inactive, R->edge_flag.p,
+                                                                       R->node_flag.p, R->stats.p);
+    post_launch(ctx);
+  }
+  finish_sweep(ctx, R);
+}
+
+}  // namespace rrtqx

@@ -1,0 +1,357 @@
+"""Handle objects over the C ABI (one class per opaque handle of rrtqx_b200.h).
+
+These are the batched, index-based calls.  The reference-shaped API
+(KDTree / kdInsert / kdFindWithinRange / explicitEdgeCheck / addNewObstacle ...)
+is layered on top in kdtree.py, collision.py and sweep.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+class Context:
+    """rrtqx_ctx: one CUDA device + stream.  Raises if no B200 is usable."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.L = A.lib()
+        h = A.vp()
+        A.check(self.L.rrtqx_ctx_create(int(device), stream, C.byref(h)), None)
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        A.check(self.L.rrtqx_ctx_sync(self.h), self.h)
+
+    def kernel_launches(self) -> int:
+        n = A.i64(0)
+        A.check(self.L.rrtqx_ctx_kernel_launches(self.h, C.byref(n)), self.h)
+        return int(n.value)
+
+    def last_phase_ms(self, phase: str) -> float:
+        ms = C.c_float(0.0)
+        A.check(self.L.rrtqx_ctx_last_phase_ms(self.h, phase.encode(), C.byref(ms)), self.h)
+        return float(ms.value)
+
+
+class RangeResult:
+    """rrtqx_range_result: device-resident neighbour lists of a query batch."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.h = A.vp()  # NULL until the first query fills it
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.rrtqx_range_result_destroy(self.h)
+            self.h = A.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sizes(self):
+        nq, tot = A.i64(0), A.i64(0)
+        A.check(self.L.rrtqx_range_result_sizes(self.h, C.byref(nq), C.byref(tot)), self.ctx.h)
+        return int(nq.value), int(tot.value)
+
+    def layout(self):
+        nq, _ = self.sizes()
+        counts = np.empty(nq, dtype=np.int32)
+        offsets = np.empty(nq, dtype=np.int64)
+        A.check(self.L.rrtqx_range_result_layout(self.h, A.ptr(counts), A.ptr(offsets)), self.ctx.h)
+        return counts, offsets
+
+    def fetch(self, want_dist=True, idx_out=None, dist_out=None):
+        _, tot = self.sizes()
+        idx = np.empty(tot, dtype=np.int32) if idx_out is None else idx_out
+        dist = (np.empty(tot, dtype=np.float64) if dist_out is None else dist_out) if want_dist else None
+        A.check(self.L.rrtqx_range_result_fetch(self.h, A.ptr(idx), A.ptr(dist)), self.ctx.h)
+        return idx, dist
+
+    def device_pointers(self):
+        p = [A.vp() for _ in range(4)]
+        A.check(self.L.rrtqx_range_result_device(self.h, *[C.byref(x) for x in p]), self.ctx.h)
+        return tuple(x.value for x in p)  # counts, offsets, idx, dist
+
+    def lists(self, want_dist=True):
+        """Python-side view: list of (idx array, dist array) per query."""
+        counts, offsets = self.layout()
+        idx, dist = self.fetch(want_dist)
+        out = []
+        for c, o in zip(counts, offsets):
+            out.append((idx[o:o + c], dist[o:o + c] if dist is not None else None))
+        return out
+
+
+class DeviceTree:
+    """rrtqx_tree: the GPU-resident KDTree (points + kd topology + grid index)."""
+
+    def __init__(self, ctx: Context, d: int, wraps=(), wrap_points=()):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.d = int(d)
+        w = np.asarray(list(wraps), dtype=np.int32)
+        wp = np.asarray(list(wrap_points), dtype=np.float64)
+        assert w.size == wp.size
+        h = A.vp()
+        A.check(self.L.rrtqx_tree_create(ctx.h, self.d, int(w.size), A.ptr(w) if w.size else None,
+                                         A.ptr(wp) if wp.size else None, C.byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_tree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        n = A.i64(0)
+        A.check(self.L.rrtqx_tree_size(self.h, C.byref(n)), self.ctx.h)
+        return int(n.value)
+
+    def insert_batch(self, positions, n=None) -> int:
+        """kdInsert for every row, in order; returns the index of the first."""
+        if isinstance(positions, np.ndarray) or not hasattr(positions, "data_ptr"):
+            positions = A.as_f64(positions, self.d)
+            n = positions.shape[0]
+        first = A.i32(0)
+        A.check(self.L.rrtqx_tree_insert_batch(self.h, A.ptr(positions), int(n), C.byref(first)), self.ctx.h)
+        return int(first.value)
+
+    def insert(self, position) -> int:
+        p = A.as_f64(position).reshape(-1)
+        assert p.size == self.d
+        idx = A.i32(0)
+        A.check(self.L.rrtqx_tree_insert(self.h, A.ptr(p), C.byref(idx)), self.ctx.h)
+        return int(idx.value)
+
+    def kd_fields(self, first=0, count=None):
+        if count is None:
+            count = len(self) - first
+        out = [np.empty(count, dtype=np.int32) for _ in range(4)]
+        A.check(self.L.rrtqx_tree_kd_fields(self.h, first, count, *[A.ptr(a) for a in out]), self.ctx.h)
+        return tuple(out)  # parent, childL, childR, split
+
+    def positions(self, first=0, count=None):
+        if count is None:
+            count = len(self) - first
+        out = np.empty((count, self.d), dtype=np.float64)
+        A.check(self.L.rrtqx_tree_positions(self.h, first, count, A.ptr(out)), self.ctx.h)
+        return out
+
+    def set_cell_occupancy(self, ppc: float):
+        A.check(self.L.rrtqx_tree_set_cell_occupancy(self.h, float(ppc)), self.ctx.h)
+
+    def reindex(self):
+        A.check(self.L.rrtqx_tree_reindex(self.h), self.ctx.h)
+
+    def range_query(self, queries, r, ranges=None, want_dist=True, count_only=False, result: RangeResult | None = None,
+                    n_queries=None):
+        """Batched kdFindWithinRange.  queries: (nq x d) numpy array or a device
+        pointer/tensor (then pass n_queries).  Returns (RangeResult, total)."""
+        if isinstance(queries, np.ndarray) or not (hasattr(queries, "data_ptr") or isinstance(queries, int)):
+            queries = A.as_f64(queries, self.d)
+            n_queries = queries.shape[0]
+        if ranges is not None and isinstance(ranges, (list, tuple, np.ndarray)):
+            ranges = A.as_f64(ranges).reshape(-1)
+            assert ranges.size == n_queries
+        if result is None:
+            result = RangeResult(self.ctx)
+        flags = (A.RANGE_WANT_DIST if want_dist else 0) | (A.RANGE_COUNT_ONLY if count_only else 0)
+        total = A.i64(0)
+        A.check(self.L.rrtqx_range_query_batch(self.h, A.ptr(queries), int(n_queries), float(r), A.ptr(ranges), flags,
+                                               C.byref(result.h), C.byref(total)), self.ctx.h)
+        return result, int(total.value)
+
+    def nearest(self, queries, n_queries=None, idx_out=None, dist_out=None):
+        """Batched kdFindNearest -> (idx int32[nq], dist float64[nq])."""
+        if isinstance(queries, np.ndarray) or not (hasattr(queries, "data_ptr") or isinstance(queries, int)):
+            queries = A.as_f64(queries, self.d)
+            n_queries = queries.shape[0]
+        idx = np.empty(n_queries, dtype=np.int32) if idx_out is None else idx_out
+        dist = np.empty(n_queries, dtype=np.float64) if dist_out is None else dist_out
+        A.check(self.L.rrtqx_nearest_batch(self.h, A.ptr(queries), int(n_queries), A.ptr(idx), A.ptr(dist)), self.ctx.h)
+        return idx, dist
+
+
+class SphereSet:
+    """rrtqx_spheres: CSpace.obstacles (List{SphereObstacle}) flattened."""
+
+    def __init__(self, ctx: Context, centers=None, radii=None, active=None):
+        self.ctx = ctx
+        self.L = ctx.L
+        h = A.vp()
+        A.check(self.L.rrtqx_spheres_create(ctx.h, C.byref(h)), ctx.h)
+        self.h = h
+        if centers is not None:
+            self.upload(centers, radii, active)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_spheres_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        n = A.i64(0)
+        A.check(self.L.rrtqx_spheres_size(self.h, C.byref(n)), self.ctx.h)
+        return int(n.value)
+
+    def upload(self, centers, radii, active=None):
+        centers = A.as_f64(centers, 3)
+        n = centers.shape[0]
+        radii = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
+        act = None if active is None else A.as_u8(np.asarray(active).astype(np.uint8))
+        A.check(self.L.rrtqx_spheres_upload(self.h, A.ptr(centers) if n else None, A.ptr(radii) if n else None,
+                                            A.ptr(act), n), self.ctx.h)
+
+    def update(self, first, radii=None, active=None):
+        count = len(radii) if radii is not None else len(active)
+        r = None if radii is None else A.as_f64(radii).reshape(-1)
+        a = None if active is None else A.as_u8(np.asarray(active).astype(np.uint8))
+        A.check(self.L.rrtqx_spheres_update(self.h, int(first), int(count), A.ptr(r), A.ptr(a)), self.ctx.h)
+
+
+def edge_check_batch(tree: DeviceTree, spheres: SphereSet, src, dst, robot_radius, flags=0, n_edges=None, out=None):
+    """Batched explicitEdgeCheck(S, edge) over edges between tree nodes."""
+    if isinstance(src, np.ndarray) or isinstance(src, (list, tuple)):
+        src, dst = A.as_i32(src), A.as_i32(dst)
+        n_edges = src.size
+    if out is None:
+        out = np.empty(n_edges, dtype=np.uint8)
+    A.check(tree.L.rrtqx_edge_check_batch(tree.h, spheres.h, A.ptr(src), A.ptr(dst), int(n_edges), float(robot_radius),
+                                          int(flags), A.ptr(out)), tree.ctx.h)
+    return out
+
+
+def segment_check_batch(ctx: Context, spheres: SphereSet, starts, ends, robot_radius, flags=0):
+    starts, ends = A.as_f64(starts, 3), A.as_f64(ends, 3)
+    n = starts.shape[0]
+    out = np.empty(n, dtype=np.uint8)
+    A.check(ctx.L.rrtqx_segment_check_batch(ctx.h, spheres.h, A.ptr(starts), A.ptr(ends), n, float(robot_radius),
+                                            int(flags), A.ptr(out)), ctx.h)
+    return out
+
+
+def node_check_batch(ctx: Context, spheres: SphereSet, points, robot_radius, flags=0):
+    """Batched explicitPointCheck -> (collide uint8[n], certificate float64[n])."""
+    points = A.as_f64(points, 3)
+    n = points.shape[0]
+    out = np.empty(n, dtype=np.uint8)
+    cert = np.empty(n, dtype=np.float64)
+    A.check(ctx.L.rrtqx_node_check_batch(ctx.h, spheres.h, A.ptr(points), n, float(robot_radius), int(flags),
+                                         A.ptr(out), A.ptr(cert)), ctx.h)
+    return out, cert
+
+
+class SweepResult:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.h = A.vp()
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.rrtqx_sweep_result_destroy(self.h)
+            self.h = A.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sizes(self):
+        v = [A.i64(0) for _ in range(4)]
+        A.check(self.L.rrtqx_sweep_result_sizes(self.h, *[C.byref(x) for x in v]), self.ctx.h)
+        return tuple(int(x.value) for x in v)  # edge_hits, node_hits, candidates, pair_tests
+
+    def fetch(self):
+        ne, nn, _, _ = self.sizes()
+        e = np.empty(ne, dtype=np.int32)
+        n = np.empty(nn, dtype=np.int32)
+        A.check(self.L.rrtqx_sweep_result_fetch(self.h, A.ptr(e), A.ptr(n)), self.ctx.h)
+        return e, n
+
+
+class EdgeSet:
+    """rrtqx_edges: device mirror of the planner's out-edge lists + parents."""
+
+    def __init__(self, tree: DeviceTree):
+        self.tree = tree
+        self.ctx = tree.ctx
+        self.L = tree.L
+        h = A.vp()
+        A.check(self.L.rrtqx_edges_create(tree.h, C.byref(h)), self.ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_edges_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        n = A.i64(0)
+        A.check(self.L.rrtqx_edges_size(self.h, C.byref(n)), self.ctx.h)
+        return int(n.value)
+
+    def upload(self, src, dst, parent=None, n_edges=None):
+        if isinstance(src, (np.ndarray, list, tuple)):
+            src, dst = A.as_i32(src), A.as_i32(dst)
+            n_edges = src.size
+        par = None if parent is None else A.as_i32(parent)
+        A.check(self.L.rrtqx_edges_upload(self.h, A.ptr(src), A.ptr(dst), int(n_edges), A.ptr(par),
+                                          0 if par is None else par.size), self.ctx.h)
+
+    def add_sweep(self, spheres: SphereSet, ob_ids, robot_radius, delta, flags=0, result: SweepResult | None = None):
+        ob_ids = A.as_i32(ob_ids)
+        if result is None:
+            result = SweepResult(self.ctx)
+        A.check(self.L.rrtqx_obstacle_add_sweep(self.h, spheres.h, A.ptr(ob_ids), ob_ids.size, float(robot_radius),
+                                                float(delta), int(flags), C.byref(result.h)), self.ctx.h)
+        return result
+
+    def remove_sweep(self, spheres: SphereSet, ob_id, other_ids, edge_dist_inf, robot_radius, delta, flags=0,
+                     result: SweepResult | None = None):
+        other_ids = A.as_i32(other_ids)
+        inf = A.as_u8(np.asarray(edge_dist_inf).astype(np.uint8))
+        if result is None:
+            result = SweepResult(self.ctx)
+        A.check(self.L.rrtqx_obstacle_remove_sweep(self.h, spheres.h, int(ob_id), A.ptr(other_ids) if other_ids.size else None,
+                                                   other_ids.size, A.ptr(inf), float(robot_radius), float(delta),
+                                                   int(flags), C.byref(result.h)), self.ctx.h)
+        return result

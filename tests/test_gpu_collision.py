@@ -1,0 +1,176 @@
+"""GPU parity: edge / node collision checks and the obstacle sweeps vs the oracle.
+Collision booleans must be bit-exact (same IEEE operations, same order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from rrtqx_3d_b200 import _abi as A
+from rrtqx_3d_b200 import workloads as W
+from rrtqx_3d_b200.device import (DeviceTree, EdgeSet, SphereSet, edge_check_batch, node_check_batch,
+                                   segment_check_batch)
+
+pytestmark = pytest.mark.gpu
+
+
+def _orc_edges(sph, ns, pts, src, dst, rho, fma=0):
+    out = np.zeros(len(src), dtype=np.uint8)
+    pts = np.ascontiguousarray(pts)
+    oracle.lib().orc_edge_check_batch(sph, ns, oracle._p(pts, oracle.c_f64p), 3, oracle._p(src, oracle.c_i32p),
+                                      oracle._p(dst, oracle.c_i32p), 0, len(src), rho, fma,
+                                      oracle._p(out, oracle.c_u8p), 4)
+    return out
+
+
+def test_edge_check_building2(ctx, building2):
+    centers, radii, _ = building2
+    pts, _, _ = W.c2_workload(20000, 1)
+    n_e = 200000
+    u = W.splitmix64(77, 0, 2 * n_e)
+    src = (u[:n_e] % np.uint64(len(pts))).astype(np.int32)
+    # mostly short edges (neighbours in index space are not neighbours in space: mix both)
+    dst = (u[n_e:] % np.uint64(len(pts))).astype(np.int32)
+    dst[::5] = src[::5]                      # zero-length edges: collide with every active obstacle (DRRT_Q.jl:1208)
+    active = np.ones(len(radii), dtype=np.uint8)
+    active[::7] = 0
+    sph, ns = oracle.make_spheres(centers, radii, unused=1 - active)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts)
+    S = SphereSet(ctx, centers, radii, active)
+    for fma in (0, 1):
+        got = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_FMA_DOT if fma else 0)
+        want = _orc_edges(sph, ns, pts, src, dst, W.ROBOT_RADIUS, fma)
+        assert np.array_equal(got, want)
+        assert got[::5].all()
+    # every obstacle forced active
+    sph_all, _ = oracle.make_spheres(centers, radii)
+    got = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_IGNORE_ACTIVE)
+    assert np.array_equal(got, _orc_edges(sph_all, ns, pts, src, dst, W.ROBOT_RADIUS))
+    # no active obstacle: nothing collides, not even zero-length edges
+    S.update(0, active=np.zeros(len(radii), dtype=np.uint8))
+    assert not edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS).any()
+
+
+def test_segment_check_short_edges_near_surfaces(ctx, building2):
+    # segments placed around the obstacle surfaces so that many land within ulps of the threshold
+    centers, radii, _ = building2
+    n = 100000
+    base = W.uniform_points(31, n, [-1.0] * 3, [1.0] * 3)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    k = np.arange(n) % len(radii)
+    scale = (radii[k] + W.ROBOT_RADIUS) * (1.0 + (W.uniform01(32, 0, n) - 0.5) * 0.02)
+    starts = centers[k] + base * scale[:, None]
+    ends = starts + W.uniform_points(33, n, [-0.5] * 3, [0.5] * 3)
+    sph, ns = oracle.make_spheres(centers, radii)
+    S = SphereSet(ctx, centers, radii)
+    got = segment_check_batch(ctx, S, starts, ends, W.ROBOT_RADIUS)
+    L = oracle.lib()
+    want = np.array([L.orc_edge_check_all(sph, ns, 0, oracle._p(np.ascontiguousarray(starts[i]), oracle.c_f64p),
+                                          oracle._p(np.ascontiguousarray(ends[i]), oracle.c_f64p), W.ROBOT_RADIUS, 0)
+                     for i in range(0, n, 10)], dtype=np.uint8)
+    assert np.array_equal(got[::10], want)
+    assert 0.2 < got.mean() < 0.8
+
+
+def test_node_check_both_variants(ctx, building2):
+    centers, radii, _ = building2
+    pts = W.uniform_points(41, 50000, [-20.0] * 3, [20.0] * 3)
+    active = np.ones(len(radii), dtype=np.uint8)
+    active[3] = 0
+    sph, ns = oracle.make_spheres(centers, radii, unused=1 - active)
+    S = SphereSet(ctx, centers, radii, active)
+    L = oracle.lib()
+    for flags, fn in ((A.CHECK_QUICK_PASS, L.orc_point_check), (0, L.orc_point_check_3d)):
+        got, cert = node_check_batch(ctx, S, pts, W.ROBOT_RADIUS, flags)
+        want = np.zeros(len(pts), dtype=np.uint8)
+        wcert = np.zeros(len(pts))
+        c = C.c_double(0.0)
+        for i in range(len(pts)):
+            want[i] = fn(sph, ns, 0, oracle._p(np.ascontiguousarray(pts[i]), oracle.c_f64p), W.ROBOT_RADIUS, C.byref(c))
+            wcert[i] = c.value
+        assert np.array_equal(got, want)
+        assert np.array_equal(cert.view(np.uint64), wcert.view(np.uint64))
+
+
+def _neighbour_graph(ctx, pts, r):
+    """All ordered pairs within r (the RRTx neighbour graph) + a parent per node."""
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts)
+    res, total = t.range_query(pts, r, want_dist=False)
+    counts, offsets = res.layout()
+    idx, _ = res.fetch(want_dist=False)
+    src = np.empty(total, dtype=np.int32)
+    for q in range(len(pts)):
+        src[offsets[q]:offsets[q] + counts[q]] = q
+    keep = src != idx
+    src, dst = src[keep], idx[keep]
+    parent = np.arange(len(pts), dtype=np.int32) - 1    # chain parents; node 0 has none
+    return t, src, dst, parent
+
+
+def test_obstacle_add_and_remove_sweep(ctx):
+    pts, _, _ = W.c2_workload(20000, 1)
+    t, src, dst, parent = _neighbour_graph(ctx, pts, 2.0)
+    centers, radii = W.c3_obstacles(12)
+    S = SphereSet(ctx, centers, radii)
+    E = EdgeSet(t)
+    E.upload(src, dst, parent)
+    ob_ids = np.arange(len(radii), dtype=np.int32)
+    res = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA)
+    ge, gn = res.fetch()
+    n_eh, n_nh, n_cand, n_tests = res.sizes()
+
+    # oracle: CSR in edge-id order per start node
+    orc = oracle.KDTree(3)
+    orc.insert_batch(pts)
+    order = np.argsort(src, kind="stable")
+    row_ptr = np.zeros(len(pts) + 1, dtype=np.int64)
+    np.add.at(row_ptr, src + 1, 1)
+    row_ptr = np.cumsum(row_ptr)
+    col = np.ascontiguousarray(dst[order])
+    eid = order.astype(np.int32)
+    L = oracle.lib()
+    blocked, orphans = set(), set()
+    tot_cand = tot_tests = 0
+    sph, _ = oracle.make_spheres(centers, radii)
+    cap = len(src) + 8
+    be = np.zeros(cap, dtype=np.int32)
+    on = np.zeros(len(pts) + 8, dtype=np.int32)
+    for o in range(len(radii)):
+        nb, no, nc, nt = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        rc = L.orc_obstacle_add_sweep(orc.h, C.byref(sph[o]), W.ROBOT_RADIUS, W.DELTA, oracle._p(row_ptr, oracle.c_i64p),
+                                      oracle._p(col, oracle.c_i32p), oracle._p(parent, oracle.c_i32p), 0,
+                                      oracle._p(be, oracle.c_i32p), C.byref(nb), cap, oracle._p(on, oracle.c_i32p),
+                                      C.byref(no), len(on), C.byref(nc), C.byref(nt))
+        assert rc == 0
+        blocked.update(eid[be[:nb.value]].tolist())
+        orphans.update(on[:no.value].tolist())
+        tot_cand += nc.value
+        tot_tests += nt.value
+    assert set(ge.tolist()) == blocked and len(ge) == len(blocked) == n_eh
+    assert set(gn.tolist()) == orphans and len(gn) == n_nh
+    assert (n_cand, n_tests) == (tot_cand, tot_tests)
+    assert len(blocked) > 100 and len(orphans) > 10
+
+    # remove obstacle 0 (Otte semantics: still active while tested): blocked edges that hit
+    # obstacle 0 and no other obstacle are restored
+    inf = np.zeros(len(src), dtype=np.uint8)
+    inf[ge] = 1
+    others = np.arange(1, len(radii), dtype=np.int32)
+    rr = E.remove_sweep(S, 0, others, inf, W.ROBOT_RADIUS, W.DELTA)
+    re_, rn_ = rr.fetch()
+    inf_csr = np.ascontiguousarray(inf[order])
+    oth, n_oth = oracle.make_spheres(centers[1:], radii[1:])
+    nr, nq = C.c_int64(0), C.c_int64(0)
+    rc = L.orc_obstacle_remove_sweep(orc.h, C.byref(sph[0]), 1, oth, n_oth, W.ROBOT_RADIUS, W.DELTA,
+                                     oracle._p(row_ptr, oracle.c_i64p), oracle._p(col, oracle.c_i32p),
+                                     oracle._p(inf_csr, oracle.c_u8p), 0, oracle._p(be, oracle.c_i32p), C.byref(nr), cap,
+                                     oracle._p(on, oracle.c_i32p), C.byref(nq), len(on))
+    assert rc == 0
+    assert set(re_.tolist()) == set(eid[be[:nr.value]].tolist())
+    assert set(rn_.tolist()) == set(on[:nq.value].tolist())
+    assert nr.value > 0
+    # QX semantics (obstacle disabled before the loop, DRRT_Q.jl:3301-3302): nothing restored
+    rq = E.remove_sweep(S, 0, others, inf, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_REMOVED_INACTIVE)
+    assert rq.sizes()[0] == 0 and rq.sizes()[1] == 0
