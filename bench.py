@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RRTQX_3D geometric hot path on B200.
+
+Metric (BASELINE.json): kd range queries/s on a 1M-node 3-D tree (config C2: 1M
+kdFindWithinRange queries at the RRTx shrinking-ball radius, neighbour indices AND
+distance keys produced), plus edge collision checks/s for the obstacle-add sweep
+(config C3) as an extra object on the same JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One process per GPU (torchrun for N > 1): the tree is replicated, every rank owns its
+own batch of queries (weak scaling, no data-path collective; per-query counts are
+all-gathered over NCCL as the fixed-size result gather).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from rrtqx_3d_b200 import workloads as W  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_range_baseline(pts, qs, r, seconds_target=12.0, nthreads=None):
+    """Oracle (CPU restatement of the reference kd tree) on a bounded sample of the workload."""
+    import oracle
+    nthreads = nthreads or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    tree = oracle.KDTree(3)
+    tree.insert_batch(pts)
+    build_s = time.perf_counter() - t0
+    probe = min(len(qs), 2000 * nthreads)
+    t0 = time.perf_counter()
+    tree.range_batch(r, qs[:probe], want_lists=True, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    rate = probe / dt
+    sample = int(min(len(qs), max(probe, rate * seconds_target)))
+    t0 = time.perf_counter()
+    counts, offsets, idx, key = tree.range_batch(r, qs[:sample], want_lists=True, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "queries/s", "cores": nthreads, "kind": "port",
+            "sample": f"first {sample} of {len(qs)} C2 queries (idx+key lists), oracle kd tree of {len(pts)} nodes "
+                      f"built in {build_s:.1f}s, {dt:.1f}s timed",
+            "mean_neighbours": float(counts.mean())}, tree
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (oracle port; Julia is not in the image)."""
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    pts, qs, r = W.c2_workload(args.nodes, args.queries)
+    import oracle
+    tree = oracle.KDTree(3)
+    tree.insert_batch(pts)
+    probe = min(len(qs), 1000 * nthreads)
+    t0 = time.perf_counter()
+    tree.range_batch(r, qs[:probe], nthreads=nthreads)
+    rate = probe / (time.perf_counter() - t0)
+    budget_s = 90.0 / max(1, args.steps + args.warmup)       # whole run within a few minutes
+    sample = int(min(len(qs), max(1000, rate * min(budget_s, 15.0))))
+    times = []
+    for it in range(args.warmup + args.steps):
+        lo = (it * sample) % max(1, len(qs) - sample + 1)
+        t0 = time.perf_counter()
+        tree.range_batch(r, qs[lo:lo + sample], nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {"impl": "reference", "metric": "kd_range_queries_per_s", "value": value, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 batched neighbour sweep (CPU arm: bounded sample per step)",
+                       "nodes": args.nodes, "queries_per_step": sample, "radius": r},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
+                             "sample": f"{sample} C2 queries per step (oracle port of kdFindWithinRange, pthreads)"},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def build_c3_edges(tree, pts, r_edge):
+    """C3 edge set: all ordered pairs (i, j), i != j, within r_edge, generated with the range kernel;
+    parent[i] = lowest-index neighbour below i, else the node's kd parent (always a lower index)."""
+    res, total = tree.range_query(pts, r_edge, want_dist=False)
+    counts, offsets = res.layout()
+    idx, _ = res.fetch(want_dist=False)
+    order = np.argsort(offsets, kind="stable")
+    src = np.empty(total, dtype=np.int32)
+    src[:] = np.repeat(order.astype(np.int32), counts[order])     # lists are packed in offset order
+    keep = src != idx
+    src, dst = np.ascontiguousarray(src[keep]), np.ascontiguousarray(idx[keep])
+    parent = tree.kd_fields()[0].copy()
+    lower = dst < src
+    cand = np.full(len(pts), np.iinfo(np.int32).max, dtype=np.int32)
+    np.minimum.at(cand, src[lower], dst[lower])
+    has = cand != np.iinfo(np.int32).max
+    parent[has] = cand[has]
+    res.close()
+    return src, dst, parent
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nodes", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=1_000_000)
+    ap.add_argument("--radius", type=float, default=None)
+    ap.add_argument("--occupancy", type=float, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sweep-edge-radius", type=float, default=0.5346)
+    ap.add_argument("--sweep-obstacles", type=int, default=256)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rrtqx_3d_b200.device import Context, DeviceTree, EdgeSet, RangeResult, SphereSet, SweepResult
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = Context(local_rank, stream.cuda_stream)
+    peak_gbs, peak_src = measured_peaks()
+
+    # ------------------------------------------------------------- workload C2
+    pts, _, r = W.c2_workload(args.nodes, 1, radius=args.radius)
+    qs = W.uniform_points(2 + rank, args.queries, [-W.ENV_RAD] * 3, [W.ENV_RAD] * 3)   # own batch per rank
+    tree = DeviceTree(ctx, 3)
+    if args.occupancy:
+        tree.set_cell_occupancy(args.occupancy)
+    tree.insert_batch(pts)
+    dq = torch.from_numpy(qs).cuda()                     # inputs resident in HBM before the timed region
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    res = RangeResult(ctx)
+    gathered = torch.empty(world * args.queries, dtype=torch.int32, device="cuda") if world > 1 else None
+
+    def step():
+        _, total = tree.range_query(dq, r, want_dist=True, result=res, n_queries=args.queries)
+        if world > 1:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink)
+            cptr = res.device_pointers()[0]
+            counts_t = tensor_from_ptr(torch, cptr, args.queries, torch.int32)
+            dist.all_gather_into_tensor(gathered, counts_t)
+        return total
+
+    def tensor_from_ptr(torch_mod, p, n, dtype):
+        # zero-copy view of library-owned device memory through the CUDA array interface
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(p), False), "version": 3}
+        return torch_mod.as_tensor(h, device="cuda")
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        total = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern = {"range_sort": [], "range_count": [], "range_scan": [], "range_fill": []}
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()                                    # L2 flush between timed iterations (outside the events)
+        a.record(stream)
+        total = step()
+        b.record(stream)
+        b.synchronize()
+        for k in kern:
+            try:
+                kern[k].append(ctx.last_phase_ms(k))
+            except Exception:
+                pass
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    ms_local = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        tmax = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        tot_t = torch.tensor([total], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot_t)
+        total_all = int(tot_t.item())
+    else:
+        ms, total_all = ms_local, total
+    value = world * args.queries / (ms / 1e3)
+
+    # roofline of the step: compulsory bytes: N*24 + Q*24 + (Q+1)*8 + K*(4+8)
+    K = total
+    alg_bytes = args.nodes * 24 + args.queries * 24 + (args.queries + 1) * 8 + K * 12
+    kern_ms = {k: float(np.mean(v)) for k, v in kern.items() if v}
+    achieved = alg_bytes / (ms_local / 1e3) / 1e9
+    fill_share = kern_ms["range_fill"] / ms_local
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                "note": "achieved = compulsory bytes of the whole range-query step / CUDA-event time of the step "
+                        "(sort+count+scan+fill); dominant kernel = range_query_kernel<3,FILL>",
+                "kernel_ms": kern_ms, "dominant_kernel_share": fill_share,
+                "dominant_kernel_frac": alg_bytes / (kern_ms["range_fill"] / 1e3) / 1e9 / peak_gbs}
+
+    line = {"metric": "kd_range_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 batched neighbour sweep: 1M-node uniform 3-D tree, kdFindWithinRange at the RRTx "
+                                   "shrinking-ball radius, idx + distance keys",
+                       "nodes": args.nodes, "queries_per_gpu": args.queries, "radius": r,
+                       "neighbours_per_step_rank0": K, "mean_neighbours": K / args.queries,
+                       "parallelism": f"replicated tree x {world} query shards", "l2_flush_between_steps": True},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps}
+
+    # ------------------------------------------------------- e2e (host buffers)
+    if not args.no_e2e:
+        hq = torch.from_numpy(qs).pin_memory()
+        h_counts = torch.empty(args.queries, dtype=torch.int32).pin_memory()
+        h_offsets = torch.empty(args.queries, dtype=torch.int64).pin_memory()
+        h_idx = torch.empty(K + 16, dtype=torch.int32).pin_memory()
+        h_dist = torch.empty(K + 16, dtype=torch.float64).pin_memory()
+        res2 = RangeResult(ctx)
+        from rrtqx_3d_b200 import _abi as A
+
+        def e2e_step():
+            # the call a user of the C ABI makes: host queries in, host lists out
+            _, tot = tree.range_query(hq.numpy(), r, want_dist=True, result=res2)
+            A.check(ctx.L.rrtqx_range_result_layout(res2.h, h_counts.data_ptr(), h_offsets.data_ptr()), ctx.h)
+            A.check(ctx.L.rrtqx_range_result_fetch(res2.h, h_idx.data_ptr(), h_dist.data_ptr()), ctx.h)
+            return tot
+
+        e2e_step()
+        n_e2e = max(2, min(args.steps, 3))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for _ in range(n_e2e):
+            tot = e2e_step()
+        eb.record(stream)
+        torch.cuda.synchronize()
+        e2e_ms = ea.elapsed_time(eb) / n_e2e
+        e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tmax = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tmax.item())
+        line["e2e"] = {"value": world * args.queries / (e2e_ms / 1e3), "unit": "queries/s",
+                       "h2d_bytes_per_step": args.queries * 24,
+                       "d2h_bytes_per_step": args.queries * 12 + tot * 12,
+                       "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
+                       "note": "pinned host queries -> rrtqx_range_query_batch -> counts/offsets/idx/dist copied to pinned host"}
+        del h_idx, h_dist
+        res2.close()
+
+    # ------------------------------------------------- extra: C3 obstacle-add sweep
+    if not args.no_sweep and rank == 0:
+        try:
+            src, dst, parent = build_c3_edges(tree, pts, args.sweep_edge_radius)
+            E = EdgeSet(tree)
+            E.upload(src, dst, parent)
+            centers, radii = W.c3_obstacles(args.sweep_obstacles)
+            S = SphereSet(ctx, centers, radii)
+            ids = np.arange(args.sweep_obstacles, dtype=np.int32)
+            sres = SweepResult(ctx)
+            times = []
+            for it in range(3 + args.steps):
+                flush.zero_()
+                E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA, result=sres)
+                if it >= 3:
+                    times.append(ctx.last_phase_ms("add_sweep"))
+            n_eh, n_nh, n_cand, n_tests = sres.sizes()
+            sms = float(np.mean(times))
+            n_e = len(src)
+            sbytes = args.nodes * 24 + n_e * 8 + args.sweep_obstacles * 40 + n_e * 1 + (n_eh + n_nh) * 4
+            line["edge_sweep"] = {"workload": "C3 obstacle-add sweep: 256 spheres vs all out-edges + parent edges of the 1M-node tree",
+                                  "edges": n_e, "obstacles": args.sweep_obstacles, "pair_checks": n_tests,
+                                  "candidate_nodes": n_cand, "blocked_edges": n_eh, "orphans": n_nh, "ms": sms,
+                                  "edges_per_s": n_e / (sms / 1e3), "pair_checks_per_s": n_tests / (sms / 1e3),
+                                  "algorithmic_bytes": sbytes, "hbm_frac": sbytes / (sms / 1e3) / 1e9 / peak_gbs}
+        except Exception as exc:  # the headline line must still be printed
+            line["edge_sweep"] = {"error": repr(exc)}
+
+    # ---------------------------------------------------------- CPU baseline
+    if not args.no_cpu and rank == 0 and world == 1:
+        base, otree = cpu_range_baseline(pts, qs, r)
+        line["cpu_baseline"] = base
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,7 @@
 // abi.cu -- extern "C" boundary of librrtqx_b200.so (include/rrtqx_b200.h).
 // Every entry point converts C++ exceptions into a status + message; there is
 // no CPU fallback anywhere behind this file.
+#include <cstdlib>
 #include <mutex>
 
 #include "objects.cuh"
@@ -124,6 +125,8 @@ rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d, int32_t num_wraps, con
     t->ctx = ctx;
     t->d = d;
     t->wrap.num_wraps = num_wraps;
+    if (const char *e = getenv("RRTQX_GRID_OCCUPANCY")) { double v = atof(e); if (v > 0.0) t->occupancy = v; }
+    if (const char *e = getenv("RRTQX_GRID_ASPECT")) { double v = atof(e); if (v >= 1.0) t->aspect = v; }
     for (int i = 0; i < num_wraps; ++i) {
       if (wraps[i] < 0 || wraps[i] >= d) { delete t; throw Error(RRTQX_ERR_INVALID, "wrap dimension out of range"); }
       t->wrap.wraps[i] = wraps[i];
