@@ -7,6 +7,7 @@
 // same s for every candidate the grid cannot exclude, and decide membership
 // with the sqrt-free but equivalent test s < T_lt(r).  sqrt is paid on hits
 // only (the returned JList key).
+#include <cmath>
 #include <cstdlib>
 
 #include "objects.cuh"
@@ -15,16 +16,23 @@
 namespace rrtqx {
 
 // ------------------------------------------------- sort queries by grid cell
+// Sort key of a query: supercell-major (S x S x S blocks of grid cells), cell
+// within the supercell minor.  Consecutive sorted queries are then spatial
+// neighbours in ALL three directions, so the queries a block works on at any
+// time share one compact candidate region (L1 reuse), and the two queries of a
+// group have almost identical candidate rows.
 template <int D>
-__global__ void query_key_kernel(GridView g, const double *__restrict__ q, int64_t nq, int32_t *__restrict__ key,
-                                 int32_t *__restrict__ hist) {
+__global__ void query_key_kernel(GridView g, int S, int nsx, int nsy, const double *__restrict__ q, int64_t nq,
+                                 int32_t *__restrict__ key, int32_t *__restrict__ hist) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const double *r = q + i * D;
   int cx = cell_of(r[0], g.lo[0], g.inv[0], g.nx);
   int cy = cell_of(r[1], g.lo[1], g.inv[1], g.ny);
   int cz = D >= 3 ? cell_of(r[2], g.lo[2], g.inv[2], g.nz) : 0;
-  int c = (cz * g.ny + cy) * g.nx + cx;
+  int sc = ((cz / S) * nsy + cy / S) * nsx + cx / S;
+  int local = ((cz % S) * S + cy % S) * S + cx % S;
+  int c = sc * (S * S * S) + local;
   key[i] = c;
   atomicAdd(&hist[c], 1);
 }
@@ -50,18 +58,21 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   cudaStream_t st = ctx->stream;
   const int TB = 256;
   r->qorder.ensure((size_t)nq, st);
-  const int ncell = t->nx * t->ny * t->nz;
-  if (t->n_sorted == 0 || nq < 2048) {
+  static int S = [] { const char *e = getenv("RRTQX_QSORT_S"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+  const int nsx = (t->nx + S - 1) / S, nsy = (t->ny + S - 1) / S, nsz = (t->nz + S - 1) / S;
+  const int64_t nbins = (int64_t)nsx * nsy * nsz * S * S * S;
+  if (t->n_sorted == 0 || nq < 2048 || nbins > (int64_t)(1 << 28)) {
     iota_kernel<<<div_up(nq, TB), TB, 0, st>>>(r->qorder.p, nq);
     post_launch(ctx);
     return;
   }
+  const int ncell = (int)nbins;
   r->qkey.ensure((size_t)nq, st);
   r->qhist.ensure((size_t)ncell + 1, st);
   r->qstart.ensure((size_t)ncell + 1, st);
   RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   GridView g = t->view();
-  query_key_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(g, dq, nq, r->qkey.p, r->qhist.p);
+  query_key_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(g, S, nsx, nsy, dq, nq, r->qkey.p, r->qhist.p);
   post_launch(ctx);
   exclusive_scan<int32_t, int32_t>(ctx, r->qhist.p, ncell, r->qstart.p, r->scan_tmp32);
   RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
@@ -297,285 +308,7 @@ static void launch_range(rrtqx_tree *t, bool fill, const double *dq, const int32
 }
 
 
-// ------------------------------------------------- fused single-pass kernel
-// One warp per group of QN consecutive (cell-sorted) queries.  Every candidate
-// is loaded once and tested against all QN queries (register tiling: halves the
-// L1/LSU traffic per test); hits are recorded as slot numbers in a per-warp
-// shared-memory buffer; when the scan of a group ends the warp reserves the
-// exact output range with ONE atomic on a global cursor and flushes densely:
-// coalesced 32-wide stores, and sqrt evaluated on hits only, all lanes busy.
-// No count pass: the tree is traversed once.  Blocks take chunks of consecutive
-// sorted queries so that the warps of a block share their candidate rows in L1.
-constexpr int FUSED_CAP = 768;      // buffered hits per query before the direct-write fallback
-constexpr int FUSED_CHUNK = 256;    // queries per block-level work item
-constexpr int FUSED_WARPS = 8;
-
-template <int D, int QN>
-struct Group {
-  double q[QN][D];
-  double T[QN];   // strict threshold on the radicand
-  double r[QN];
-  int qid[QN];
-};
-
-// Scan all candidates of the group.  DIRECT = false: append hit slots to buf
-// (up to FUSED_CAP per query), cnt[] = number of hits.  DIRECT = true: write
-// results at base[k] + ordinal (used when a query overflowed its buffer).
-// Slots: j >= 0 is a position in the cell-sorted arrays, j < 0 encodes node
-// -(j+1) of the unsorted tail.
-template <int D, int QN, bool DIRECT>
-__device__ __forceinline__ void scan_group(const GridView &g, const Group<D, QN> &G, int lane, unsigned lt,
-                                           int *__restrict__ buf, int (&cnt)[QN], const int64_t (&base)[QN],
-                                           int32_t *__restrict__ out_idx, double *__restrict__ out_dist) {
-#pragma unroll
-  for (int k = 0; k < QN; ++k) cnt[k] = 0;
-
-  auto visit = [&](bool valid, int slot, double px, double py, double pz, double pw) {
-#pragma unroll
-    for (int k = 0; k < QN; ++k) {
-      const double s = sqdist<D>(G.q[k], px, py, pz, pw);
-      const bool hit = valid && (s < G.T[k]);
-      const unsigned m = __ballot_sync(FULL, hit);
-      if (hit) {
-        const int o = cnt[k] + __popc(m & lt);
-        if (DIRECT) {
-          out_idx[base[k] + o] = slot >= 0 ? g.sperm[slot] : -(slot + 1);
-          if (out_dist) out_dist[base[k] + o] = __dsqrt_rn(s);
-        } else if (o < FUSED_CAP) {
-          buf[k * FUSED_CAP + o] = slot;
-        }
-      }
-      cnt[k] += __popc(m);
-    }
-  };
-
-  if (g.n_sorted > 0) {
-    // union of the groups' row ranges
-    int cy0 = 0x7fffffff, cy1 = -1, cz0 = 0x7fffffff, cz1 = -1;
-#pragma unroll
-    for (int k = 0; k < QN; ++k) {
-      if (!(G.r[k] > 0.0)) continue;
-      const double ri = G.r[k] * (1.0 + 1e-9);
-      cy0 = min(cy0, cell_of(G.q[k][1] - ri, g.lo[1], g.inv[1], g.ny));
-      cy1 = max(cy1, cell_of(G.q[k][1] + ri, g.lo[1], g.inv[1], g.ny));
-      if (D >= 3) {
-        cz0 = min(cz0, cell_of(G.q[k][2] - ri, g.lo[2], g.inv[2], g.nz));
-        cz1 = max(cz1, cell_of(G.q[k][2] + ri, g.lo[2], g.inv[2], g.nz));
-      } else {
-        cz0 = 0; cz1 = 0;
-      }
-    }
-    if (cy1 >= cy0 && cz1 >= cz0) {
-      const int wy = cy1 - cy0 + 1;
-      const int nrows = wy * (cz1 - cz0 + 1);
-      for (int rb = 0; rb < nrows; rb += 32) {
-        int sa = 0x7fffffff, sb = 0;  // union span of this lane's row over the group
-        const int row = rb + lane;
-        if (row < nrows) {
-          const int cy = cy0 + row % wy, cz = cz0 + row / wy;
-#pragma unroll
-          for (int k = 0; k < QN; ++k) {
-            if (!(G.r[k] > 0.0)) continue;
-            const double ri = G.r[k] * (1.0 + 1e-9);
-            RowSpan sp = row_span<D>(g, G.q[k], ri, ri * ri, cy, cz);
-            if (sp.end > sp.start) { sa = min(sa, sp.start); sb = max(sb, sp.end); }
-          }
-        }
-        if (sb <= sa) { sa = 0; sb = 0; }
-        const int lim = min(32, nrows - rb);
-        for (int t = 0; t < lim; ++t) {
-          const int a = __shfl_sync(FULL, sa, t);
-          const int b = __shfl_sync(FULL, sb, t);
-          int j0 = a;
-          // two candidates per lane per trip: independent dependency chains
-          for (; j0 + 32 < b; j0 += 64) {
-            const int ja = j0 + lane, jb = j0 + 32 + lane;
-            const bool vb = jb < b;
-            const double xa = g.sx[ja], ya = g.sy[ja], za = D >= 3 ? g.sz[ja] : 0.0, wa = D >= 4 ? g.sw[ja] : 0.0;
-            const int jbc = vb ? jb : ja;
-            const double xb = g.sx[jbc], yb = g.sy[jbc], zb = D >= 3 ? g.sz[jbc] : 0.0, wb = D >= 4 ? g.sw[jbc] : 0.0;
-            visit(true, ja, xa, ya, za, wa);
-            visit(vb, jb, xb, yb, zb, wb);
-          }
-          if (j0 < b) {
-            const int j = j0 + lane;
-            const bool v = j < b;
-            const int jc = v ? j : a;
-            visit(v, j, g.sx[jc], g.sy[jc], D >= 3 ? g.sz[jc] : 0.0, D >= 4 ? g.sw[jc] : 0.0);
-          }
-        }
-      }
-    }
-  }
-  for (int j0 = g.n_sorted; j0 < g.n_total; j0 += 32) {  // unsorted tail of recent inserts
-    const int j = j0 + lane;
-    const bool v = j < g.n_total;
-    double4 p = make_double4(0, 0, 0, 0);
-    if (v) p = g.pos[j];
-    visit(v, -(j + 1), p.x, p.y, p.z, p.w);
-  }
-}
-
-template <int D, int QN>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 2)
-range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t *__restrict__ qorder, int64_t nq,
-                   double r_uniform, const double *__restrict__ ranges, int32_t *__restrict__ counts,
-                   int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx, double *__restrict__ out_dist,
-                   unsigned long long cap, unsigned long long *__restrict__ cursor /* [0] output, [1] chunk */,
-                   int write_lists) {
-  extern __shared__ int s_buf[];  // [FUSED_WARPS][QN][FUSED_CAP]
-  __shared__ unsigned long long s_chunk;
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned lt = lanemask_lt();
-  int *buf = s_buf + warp * QN * FUSED_CAP;
-
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&cursor[1], 1ull);
-    __syncthreads();
-    const int64_t chunk_base = (int64_t)s_chunk * FUSED_CHUNK;
-    if (chunk_base >= nq) break;
-
-    for (int p = warp; p * QN < FUSED_CHUNK; p += FUSED_WARPS) {
-      const int64_t qfirst = chunk_base + (int64_t)p * QN;
-      if (qfirst >= nq) break;
-      Group<D, QN> G;
-      bool root_extra[QN];
-      double root_s = 0.0;
-#pragma unroll
-      for (int k = 0; k < QN; ++k) {
-        const bool have = qfirst + k < nq;
-        G.qid[k] = have ? qorder[qfirst + k] : -1;
-        const int qq = have ? G.qid[k] : G.qid[0];
-#pragma unroll
-        for (int c = 0; c < D; ++c) G.q[k][c] = queries[(int64_t)qq * D + c];
-        G.r[k] = have ? (ranges ? ranges[qq] : r_uniform) : -1.0;
-        G.T[k] = sqrt_thresh_lt(G.r[k]);
-        // root (node 0) is admitted with <= (kdTree_general.jl:896-898): it needs
-        // an explicit entry only when it sits exactly at distance r
-        const double4 p0 = g.pos[0];
-        const double s0 = sqdist<D>(G.q[k], p0.x, p0.y, p0.z, p0.w);
-        root_extra[k] = have && (__dsqrt_rn(s0) <= G.r[k]) && !(s0 < G.T[k]);
-        if (root_extra[k]) root_s = s0;
-      }
-      int cnt[QN];
-      int64_t base[QN];
-#pragma unroll
-      for (int k = 0; k < QN; ++k) base[k] = 0;
-      scan_group<D, QN, false>(g, G, lane, lt, buf, cnt, base, nullptr, nullptr);
-
-      // reserve the exact output range of the group: one atomic per group
-      unsigned long long need = 0;
-#pragma unroll
-      for (int k = 0; k < QN; ++k) need += (unsigned long long)(cnt[k] + (root_extra[k] ? 1 : 0));
-      unsigned long long b0 = 0;
-      if (lane == 0) b0 = atomicAdd(&cursor[0], need);
-      b0 = __shfl_sync(FULL, b0, 0);
-      bool overflow = false;
-#pragma unroll
-      for (int k = 0; k < QN; ++k) {
-        base[k] = (int64_t)b0;
-        b0 += (unsigned long long)(cnt[k] + (root_extra[k] ? 1 : 0));
-        if (cnt[k] > FUSED_CAP) overflow = true;
-        if (lane == 0 && G.qid[k] >= 0) {
-          counts[G.qid[k]] = cnt[k] + (root_extra[k] ? 1 : 0);
-          offsets[G.qid[k]] = base[k];
-        }
-      }
-      if (!write_lists || b0 > cap) continue;  // counts only, or the lists do not fit (host retries)
-      if (overflow) {
-        int cnt2[QN];
-        scan_group<D, QN, true>(g, G, lane, lt, buf, cnt2, base, out_idx, out_dist);
-      } else {
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < QN; ++k) {
-          for (int h = lane; h < cnt[k]; h += 32) {  // dense flush: all lanes hold a hit
-            const int slot = buf[k * FUSED_CAP + h];
-            double px, py, pz = 0.0, pw = 0.0;
-            int node;
-            if (slot >= 0) {
-              px = g.sx[slot]; py = g.sy[slot];
-              if (D >= 3) pz = g.sz[slot];
-              if (D >= 4) pw = g.sw[slot];
-              node = g.sperm[slot];
-            } else {
-              node = -(slot + 1);
-              const double4 pp = g.pos[node];
-              px = pp.x; py = pp.y; pz = pp.z; pw = pp.w;
-            }
-            out_idx[base[k] + h] = node;
-            if (out_dist) out_dist[base[k] + h] = __dsqrt_rn(sqdist<D>(G.q[k], px, py, pz, pw));
-          }
-        }
-        __syncwarp();
-      }
-#pragma unroll
-      for (int k = 0; k < QN; ++k)
-        if (root_extra[k] && lane == 0) {
-          out_idx[base[k] + cnt[k]] = 0;
-          if (out_dist) out_dist[base[k] + cnt[k]] = __dsqrt_rn(root_s);
-        }
-    }
-  }
-}
-
-template <int D>
-static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr, int64_t nq, double r, uint32_t flags,
-                              rrtqx_range_result *res) {
-  rrtqx_ctx *ctx = t->ctx;
-  cudaStream_t st = ctx->stream;
-  constexpr int QN = 2;
-  const bool count_only = flags & RRTQX_RANGE_COUNT_ONLY;
-  const bool want_dist = flags & RRTQX_RANGE_WANT_DIST;
-  res->cursor.ensure(4, st);
-  {
-    PhaseScope p2(ctx, "range_sort");
-    sort_queries<D>(t, res, dq, nq);
-  }
-  const size_t smem = (size_t)FUSED_WARPS * QN * FUSED_CAP * sizeof(int);
-  static bool attr_set[5] = {false, false, false, false, false};
-  if (!attr_set[D]) {
-    RQ_CUDA(cudaFuncSetAttribute(range_fused_kernel<D, QN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[D] = true;
-  }
-  const int blocks = (int)std::min<int64_t>((nq + FUSED_CHUNK - 1) / FUSED_CHUNK, (int64_t)ctx->sm_count * 2);
-  // Output capacity: grow-only buffers sized by the previous results; if the
-  // lists do not fit, the pass still yields exact counts + total and is
-  // repeated once with the exact size (first call / growing workloads only).
-  size_t cap = count_only ? 0 : res->idx.cap;
-  if (!count_only && want_dist) cap = std::min(cap, res->dist.cap);
-  if (!count_only && cap == 0) {
-    cap = (size_t)nq * 64;
-    res->idx.ensure(cap, st, 0, 1.0);
-    if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
-    cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
-  }
-  unsigned long long total = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    GridView g = t->view();
-    RQ_CUDA(cudaMemsetAsync(res->cursor.p, 0, 4 * sizeof(unsigned long long), st));
-    {
-      PhaseScope p2(ctx, "range_fill");
-      range_fused_kernel<D, QN><<<blocks, FUSED_WARPS * 32, smem, st>>>(
-          g, dq, res->qorder.p, nq, r, dr, res->counts.p, res->offsets.p, res->idx.p,
-          want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p, count_only ? 0 : 1);
-      post_launch(ctx);
-    }
-    RQ_CUDA(cudaMemcpyAsync(&total, res->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, st));
-    RQ_CUDA(cudaStreamSynchronize(st));
-    if (count_only || total <= cap) break;
-    RQ_REQUIRE(attempt == 0, "internal: range output did not fit after resizing");
-    cap = (size_t)total + (size_t)(total / 32) + 1024;
-    res->idx.ensure(cap, st, 0, 1.0);
-    if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
-    cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
-  }
-  res->n_queries = nq;
-  res->total = (int64_t)total;
-  res->has_lists = !count_only;
-  res->has_dist = !count_only && want_dist;
-}
+#include "range_fused.cuh"
 
 template <int D>
 static void range_query_impl(rrtqx_tree *t, const double *queries, int64_t nq, double r, const double *ranges,

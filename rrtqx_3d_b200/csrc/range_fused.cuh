@@ -1,0 +1,508 @@
+// range_fused.cuh -- single-pass batched kdFindWithinRange (included by range.cu,
+// inside namespace rrtqx).
+//
+// One warp per group of QN consecutive (cell-sorted) queries:
+//   * the candidate region is the set of grid rows (runs of cells along x)
+//     that can hold a point within r; it is computed conservatively in FP32
+//     cell units (margins far above the rounding error), never deciding a
+//     result -- membership is always the exact FP64 test s < T_lt(r);
+//   * rows are short (fine cells give tight culling), so a warp works on
+//     32/W rows at once: W-lane sub-groups each walk one row;
+//   * every candidate is loaded once and tested against all QN queries;
+//   * hits are recorded as slot numbers in a per-warp shared-memory buffer;
+//     when the scan ends the warp reserves the exact output range with ONE
+//     atomic on a global cursor and flushes densely: coalesced 32-wide
+//     stores, sqrt evaluated on hits only with all lanes busy.
+// The tree is traversed once (no count pass).  Blocks own chunks of
+// consecutive sorted queries so their warps share candidate rows in L1.
+
+constexpr int FUSED_CAP = 576;    // buffered hits per query before the direct-write fallback
+constexpr int FUSED_TAB = 256;    // octet-table entries per warp
+constexpr int FUSED_ROUNDS = 4;   // groups each warp takes from one block-level chunk
+
+__device__ __forceinline__ void sts32(unsigned addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// keeps a value in a register (stops the compiler from re-deriving it from
+// special registers inside the hot loop)
+__device__ __forceinline__ unsigned pin_reg(unsigned v) {
+  unsigned r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <int D, int QN>
+struct Group {
+  double q[QN][D];
+  double T[QN];  // strict threshold on the radicand: hit <=> s < T
+  float ff[QN][3];  // query position in (fractional) cell coordinates
+  float r2f[QN];    // inflated r^2 (FP32, conservative)
+  float rf[QN];     // inflated r
+  int qid[QN];
+  bool live[QN];    // query exists and r > 0
+};
+
+struct FGrid {
+  float inv[3], cell[3];
+};
+
+__device__ __forceinline__ int clampi(float v, int n) {  // floor + clamp to [0, n-1]; NaN -> 0
+  return (int)fminf(fmaxf(floorf(v), 0.0f), (float)(n - 1));
+}
+
+// Conservative cell range [cxa, cxb] of row (cy,cz) that can hold a point
+// within r of the query; false if the row is out of reach.
+template <int D>
+__device__ __forceinline__ bool row_cells(const GridView &g, const FGrid &fg, const float *ff, float r2f, int cy, int cz,
+                                          int &cxa, int &cxb) {
+  // lower bounds of |p.y - q.y|, |p.z - q.z| in cell units; boundary rows also
+  // hold the points clamped in from beyond the grid, so they give no bound on
+  // that side.  1e-3 cells of slack covers the FP32 error of ff (coordinates
+  // up to 1024 cells: ulp 6e-5) and the FP64 rounding of cell_of().
+  const float ninf = -INFINITY;
+  float dyc = fmaxf(cy == 0 ? ninf : (float)cy - ff[1], cy == g.ny - 1 ? ninf : ff[1] - (float)(cy + 1));
+  dyc = fmaxf(dyc - 1e-3f, 0.0f);
+  const float dy = dyc * fg.cell[1];
+  float rem = r2f - dy * dy;
+  if (D >= 3) {
+    float dzc = fmaxf(cz == 0 ? ninf : (float)cz - ff[2], cz == g.nz - 1 ? ninf : ff[2] - (float)(cz + 1));
+    dzc = fmaxf(dzc - 1e-3f, 0.0f);
+    const float dz = dzc * fg.cell[2];
+    rem -= dz * dz;
+  }
+  if (isinf(r2f)) {  // unbounded query: whole row
+    cxa = 0;
+    cxb = g.nx - 1;
+    return true;
+  }
+  if (!(rem >= 0.0f)) return false;
+  const float xc = sqrtf(rem) * (1.0f + 1e-5f) * fg.inv[0] + 1e-3f;
+  cxa = clampi(ff[0] - xc, g.nx);
+  cxb = clampi(ff[0] + xc, g.nx);
+  return true;
+}
+
+// Scan all candidates of the group.  DIRECT = false: append hit slots to the
+// warp's shared buffer (up to FUSED_CAP per query), cnt[] = number of hits.
+// DIRECT = true: write results at base[k] + ordinal (a query overflowed its
+// buffer).  Slots: j >= 0 is a position in the cell-sorted arrays, j < 0
+// encodes node -(j+1) of the unsorted tail.
+//
+// The candidate rows are short (fine cells), so they are flattened into a table
+// of "octets" (start slot, 1..8 valid points) in shared memory; each 8-lane
+// sub-group then takes one octet per trip, which keeps every sub-group busy
+// whatever the row lengths are.
+template <int D, int QN, bool DIRECT>
+__device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, const Group<D, QN> &G, int lane,
+                                           unsigned lt, unsigned sbuf, unsigned stab, int (&cnt)[QN],
+                                           const int64_t (&base)[QN], int32_t *__restrict__ out_idx,
+                                           double *__restrict__ out_dist) {
+#pragma unroll
+  for (int k = 0; k < QN; ++k) cnt[k] = 0;
+  const double *__restrict__ sx = g.sx;
+  const double *__restrict__ sy = g.sy;
+  const double *__restrict__ sz = g.sz;
+  const double *__restrict__ sw = g.sw;
+
+  auto visit = [&](bool valid, int slot, double px, double py, double pz, double pw) {
+#pragma unroll
+    for (int k = 0; k < QN; ++k) {
+      const double s = sqdist<D>(G.q[k], px, py, pz, pw);
+      const bool hit = valid && (s < G.T[k]);
+      const unsigned m = __ballot_sync(FULL, hit);
+      const int o = cnt[k] + __popc(m & lt);
+      if (DIRECT) {
+        if (hit) {
+          out_idx[base[k] + o] = slot >= 0 ? g.sperm[slot] : -(slot + 1);
+          if (out_dist) out_dist[base[k] + o] = __dsqrt_rn(s);
+        }
+      } else {
+        if (hit && o < FUSED_CAP) sts32(sbuf + 4u * (unsigned)(k * FUSED_CAP + o), slot);
+      }
+      cnt[k] += __popc(m);
+    }
+  };
+
+  // walk the octet table: sub-group grp takes entry 4*it + grp
+  const int grp = lane >> 3, sub = lane & 7;
+  auto process_table = [&](int n_ent) {
+    __syncwarp();
+    // U trips per loop iteration: all 3*U candidate loads are issued before the
+    // first test, so one memory latency is paid per U trips, not per trip.
+    constexpr int U = 4;
+    for (int e0 = grp; e0 < n_ent + grp; e0 += 4 * U) {   // uniform trip count: (e0 - grp) < n_ent
+      int jj[U];
+      bool vv[U];
+      double px[U], py[U], pz[U], pw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + 4 * u;
+        const int ent = e < n_ent ? lds32(stab + 4u * (unsigned)e) : 0;
+        vv[u] = sub < (ent & 15);
+        jj[u] = vv[u] ? (ent >> 4) + sub : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        px[u] = sx[jj[u]];
+        py[u] = sy[jj[u]];
+        pz[u] = D >= 3 ? sz[jj[u]] : 0.0;
+        pw[u] = D >= 4 ? sw[jj[u]] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (e0 - grp + 4 * u < n_ent)   // warp-uniform: skip trips past the end of the table
+          visit(vv[u], jj[u], px[u], py[u], pz[u], pw[u]);
+      }
+    }
+    __syncwarp();
+  };
+
+  bool any_live = false;
+#pragma unroll
+  for (int k = 0; k < QN; ++k) any_live |= G.live[k];
+
+  if (g.n_sorted > 0 && any_live) {
+    // union of the group's row ranges
+    int cy0 = 0x7fffffff, cy1 = -1, cz0 = 0x7fffffff, cz1 = -1;
+#pragma unroll
+    for (int k = 0; k < QN; ++k) {
+      if (!G.live[k]) continue;
+      const float ry = G.rf[k] * fg.inv[1] + 1e-3f;
+      cy0 = min(cy0, clampi(G.ff[k][1] - ry, g.ny));
+      cy1 = max(cy1, clampi(G.ff[k][1] + ry, g.ny));
+      if (D >= 3) {
+        const float rz = G.rf[k] * fg.inv[2] + 1e-3f;
+        cz0 = min(cz0, clampi(G.ff[k][2] - rz, g.nz));
+        cz1 = max(cz1, clampi(G.ff[k][2] + rz, g.nz));
+      } else {
+        cz0 = 0;
+        cz1 = 0;
+      }
+    }
+    const int wy = cy1 - cy0 + 1;
+    const int nrows = wy * (cz1 - cz0 + 1);
+    int tot = 0;  // entries currently in the table
+    for (int rb = 0; rb < nrows; rb += 32) {
+      // lane <-> row: union over the group's queries of the reachable cells
+      int sa = 0, sb = 0;
+      const int row = rb + lane;
+      if (row < nrows) {
+        const int cy = cy0 + row % wy, cz = cz0 + row / wy;
+        int ca = 0x7fffffff, cb = -1;
+#pragma unroll
+        for (int k = 0; k < QN; ++k) {
+          if (!G.live[k]) continue;
+          int a, b;
+          if (row_cells<D>(g, fg, G.ff[k], G.r2f[k], cy, cz, a, b)) { ca = min(ca, a); cb = max(cb, b); }
+        }
+        if (cb >= ca) {
+          const int rbase = (cz * g.ny + cy) * g.nx;
+          sa = g.cell_start[rbase + ca];
+          sb = g.cell_start[rbase + cb + 1];
+        }
+      }
+      // emit this batch's octets, draining the table whenever it fills up
+      int todo = (sb - sa + 7) >> 3;  // octets of my row still to emit
+      for (;;) {
+        int incl = todo;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int sum = __shfl_sync(FULL, incl, 31);
+        if (sum == 0) break;
+        const int pos = incl - todo;
+        const int room = FUSED_TAB - tot;
+        const int mine = max(0, min(todo, room - pos));
+        for (int k = 0; k < mine; ++k) {
+          const int n = min(8, sb - sa);
+          sts32(stab + 4u * (unsigned)(tot + pos + k), (sa << 4) | n);
+          sa += 8;
+        }
+        todo -= mine;
+        tot += min(sum, room);
+        if (sum <= room) break;
+        process_table(tot);
+        tot = 0;
+      }
+    }
+    if (tot > 0) process_table(tot);
+  }
+  if (any_live)
+    for (int j0 = g.n_sorted; j0 < g.n_total; j0 += 32) {  // unsorted tail of recent inserts
+      const int j = j0 + lane;
+      const bool v = j < g.n_total;
+      double4 p = make_double4(0, 0, 0, 0);
+      if (v) p = g.pos[j];
+      visit(v, -(j + 1), p.x, p.y, p.z, p.w);
+    }
+}
+
+// Dense flush of one query's buffered hits: all lanes hold a hit.
+template <int D, bool TAIL>
+__device__ __forceinline__ void flush_hits(const GridView &g, const double *q, unsigned sbuf_k, int n, int lane,
+                                           int32_t *__restrict__ oi, double *__restrict__ od) {
+  const double *__restrict__ sx = g.sx;
+  const double *__restrict__ sy = g.sy;
+  const double *__restrict__ sz = g.sz;
+  const double *__restrict__ sw = g.sw;
+  const int *__restrict__ sperm = g.sperm;
+  constexpr int U = 4;
+  for (int h0 = lane; h0 < n + lane; h0 += 32 * U) {   // (h0 - lane) < n: uniform trips
+    int node[U];
+    double px[U], py[U], pz[U], pw[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int h = h0 + 32 * u;
+      ok[u] = h < n;
+      const int slot = ok[u] ? lds32(sbuf_k + 4u * (unsigned)h) : 0;
+      px[u] = 0.0;
+      py[u] = 0.0;
+      pz[u] = 0.0;
+      pw[u] = 0.0;
+      node[u] = 0;
+      if (!ok[u]) continue;   // nothing to load (the sorted arrays may not even exist)
+      if (!TAIL || slot >= 0) {
+        px[u] = sx[slot];
+        py[u] = sy[slot];
+        if (D >= 3) pz[u] = sz[slot];
+        if (D >= 4) pw[u] = sw[slot];
+        node[u] = sperm[slot];
+      } else {
+        node[u] = -(slot + 1);
+        const double4 pp = g.pos[node[u]];
+        px[u] = pp.x; py[u] = pp.y; pz[u] = pp.z; pw[u] = pp.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int h = h0 + 32 * u;
+      if (ok[u]) {
+        oi[h] = node[u];
+        if (od) od[h] = __dsqrt_rn(sqdist<D>(q, px[u], py[u], pz[u], pw[u]));
+      }
+    }
+  }
+}
+
+template <int D, int QN, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t *__restrict__ qorder, int64_t nq,
+                   double r_uniform, double T_uniform, const double *__restrict__ ranges,
+                   const double *__restrict__ Tq, int32_t *__restrict__ counts, int64_t *__restrict__ offsets,
+                   int32_t *__restrict__ out_idx, double *__restrict__ out_dist, unsigned long long cap,
+                   unsigned long long *__restrict__ cursor, int write_lists) {
+  extern __shared__ int s_buf[];  // [NW][QN][FUSED_CAP] hit slots, then [NW][FUSED_TAB] octet tables
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(s_buf);
+  const unsigned sbuf = pin_reg(s0 + 4u * (unsigned)(warp * QN * FUSED_CAP));
+  const unsigned stab = pin_reg(s0 + 4u * (unsigned)(NW * QN * FUSED_CAP + warp * FUSED_TAB));
+  FGrid fg;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { fg.inv[c] = (float)g.inv[c]; fg.cell[c] = (float)g.cell[c]; }
+  const double4 p0 = g.pos[0];
+  const bool has_tail = g.n_total > g.n_sorted;
+
+  constexpr int CHUNK = NW * QN * FUSED_ROUNDS;
+  const int64_t n_chunks = (nq + CHUNK - 1) / CHUNK;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t chunk_base = chunk * CHUNK;
+    for (int rnd = 0; rnd < FUSED_ROUNDS; ++rnd) {
+      const int64_t qfirst = chunk_base + (int64_t)(rnd * NW + warp) * QN;
+      if (qfirst >= nq) break;
+      Group<D, QN> G;
+      bool root_extra[QN];
+      double root_s = 0.0;
+#pragma unroll
+      for (int k = 0; k < QN; ++k) {
+        const bool have = qfirst + k < nq;
+        G.qid[k] = have ? qorder[qfirst + k] : -1;
+        const int qq = have ? G.qid[k] : G.qid[0];
+#pragma unroll
+        for (int c = 0; c < D; ++c) G.q[k][c] = queries[(int64_t)qq * D + c];
+        const double r = have ? (ranges ? ranges[qq] : r_uniform) : -1.0;
+        G.T[k] = have ? (Tq ? Tq[qq] : T_uniform) : -1.0;
+        G.live[k] = have && (r > 0.0);
+        const double ri = r * (1.0 + 1e-9);
+        G.rf[k] = __double2float_ru(ri) * (1.0f + 1e-6f);
+        G.r2f[k] = __double2float_ru(ri * ri) * (1.0f + 1e-5f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          G.ff[k][c] = c < D ? (float)((G.q[k][c] - g.lo[c]) * g.inv[c]) : 0.0f;
+        // root (node 0) is admitted with <= (kdTree_general.jl:896-898): it needs
+        // an explicit entry only when it sits exactly at distance r
+        const double sr = sqdist<D>(G.q[k], p0.x, p0.y, p0.z, p0.w);
+        root_extra[k] = have && !(sr < G.T[k]) && (__dsqrt_rn(sr) <= r);
+        if (root_extra[k]) root_s = sr;
+      }
+      int cnt[QN];
+      int64_t base[QN];
+#pragma unroll
+      for (int k = 0; k < QN; ++k) base[k] = 0;
+      scan_group<D, QN, false>(g, fg, G, lane, lt, sbuf, stab, cnt, base, nullptr, nullptr);
+
+      // reserve the exact output range of the group: one atomic per group
+      unsigned long long need = 0;
+#pragma unroll
+      for (int k = 0; k < QN; ++k) need += (unsigned long long)(cnt[k] + (root_extra[k] ? 1 : 0));
+      unsigned long long b0 = 0;
+      if (lane == 0) b0 = atomicAdd(&cursor[0], need);
+      b0 = __shfl_sync(FULL, b0, 0);
+      bool overflow = false;
+#pragma unroll
+      for (int k = 0; k < QN; ++k) {
+        base[k] = (int64_t)b0;
+        b0 += (unsigned long long)(cnt[k] + (root_extra[k] ? 1 : 0));
+        if (cnt[k] > FUSED_CAP) overflow = true;
+        if (lane == 0 && G.qid[k] >= 0) {
+          counts[G.qid[k]] = cnt[k] + (root_extra[k] ? 1 : 0);
+          offsets[G.qid[k]] = base[k];
+        }
+      }
+      if (!write_lists || b0 > cap) continue;  // counts only, or the lists do not fit (host retries)
+      if (overflow) {
+        int cnt2[QN];
+        scan_group<D, QN, true>(g, fg, G, lane, lt, sbuf, stab, cnt2, base, out_idx, out_dist);
+      } else {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < QN; ++k) {
+          const unsigned sb_k = sbuf + 4u * (unsigned)(k * FUSED_CAP);
+          if (has_tail)
+            flush_hits<D, true>(g, G.q[k], sb_k, cnt[k], lane, out_idx + base[k], out_dist ? out_dist + base[k] : nullptr);
+          else
+            flush_hits<D, false>(g, G.q[k], sb_k, cnt[k], lane, out_idx + base[k], out_dist ? out_dist + base[k] : nullptr);
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int k = 0; k < QN; ++k)
+        if (root_extra[k] && lane == 0) {
+          out_idx[base[k] + cnt[k]] = 0;
+          if (out_dist) out_dist[base[k] + cnt[k]] = __dsqrt_rn(root_s);
+        }
+    }
+  }
+}
+
+__global__ void thresh_kernel(const double *__restrict__ ranges, int64_t n, double *__restrict__ Tq) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) Tq[i] = sqrt_thresh_lt(ranges[i]);
+}
+
+// Host twin of sqrt_thresh_lt (std::sqrt is correctly rounded, like __dsqrt_rn).
+static double host_sqrt_thresh_lt(double r) {
+  if (r != r) return r;
+  if (r <= 0.0) return 0.0;
+  if (std::isinf(r)) return r;
+  double t = r * r;
+  if (std::isinf(t)) {
+    t = 1.7976931348623157e308;
+    if (std::sqrt(t) < r) return INFINITY;
+  }
+  while (t > 0.0 && std::sqrt(t) >= r) t = std::nextafter(t, -INFINITY);
+  while (std::sqrt(t) < r) t = std::nextafter(t, INFINITY);
+  return t;
+}
+
+struct FusedTuning {
+  int qn = 2;
+  int nw = 24;
+};
+static FusedTuning fused_tuning() {
+  FusedTuning f;
+  if (const char *e = getenv("RRTQX_FUSED_QN")) f.qn = atoi(e);
+  if (const char *e = getenv("RRTQX_FUSED_NW")) f.nw = atoi(e);
+  return f;
+}
+
+template <int D, int QN, int NW>
+static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, const int32_t *qorder, int64_t nq,
+                         double r, double T, const double *dr, const double *dT, int32_t *counts, int64_t *offsets,
+                         int32_t *idx, double *dist, unsigned long long cap, unsigned long long *cursor,
+                         int write_lists) {
+  const size_t smem = (size_t)NW * (QN * FUSED_CAP + FUSED_TAB) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RQ_CUDA(cudaFuncSetAttribute(range_fused_kernel<D, QN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  constexpr int CHUNK = NW * QN * FUSED_ROUNDS;
+  const int64_t n_chunks = (nq + CHUNK - 1) / CHUNK;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)ctx->sm_count));
+  range_fused_kernel<D, QN, NW><<<blocks, NW * 32, smem, ctx->stream>>>(g, dq, qorder, nq, r, T, dr, dT, counts, offsets,
+                                                                        idx, dist, cap, cursor, write_lists);
+  post_launch(ctx);
+}
+
+template <int D>
+static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr, int64_t nq, double r, uint32_t flags,
+                              rrtqx_range_result *res) {
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  const bool count_only = flags & RRTQX_RANGE_COUNT_ONLY;
+  const bool want_dist = flags & RRTQX_RANGE_WANT_DIST;
+  res->cursor.ensure(4, st);
+  {
+    PhaseScope p2(ctx, "range_sort");
+    sort_queries<D>(t, res, dq, nq);
+  }
+  const double T = host_sqrt_thresh_lt(r);
+  const double *dT = nullptr;
+  if (dr) {
+    res->tq.ensure((size_t)nq, st);
+    thresh_kernel<<<div_up(nq, 256), 256, 0, st>>>(dr, nq, res->tq.p);
+    post_launch(ctx);
+    dT = res->tq.p;
+  }
+  // Output capacity: grow-only buffers sized by the previous results; if the
+  // lists do not fit, the pass still yields exact counts + total and is
+  // repeated once with the exact size (first call / growing workloads only).
+  size_t cap = count_only ? 0 : res->idx.cap;
+  if (!count_only && want_dist) cap = std::min(cap, res->dist.cap);
+  if (!count_only && cap == 0) {
+    cap = (size_t)nq * 64;
+    res->idx.ensure(cap, st, 0, 1.0);
+    if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
+    cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
+  }
+  const FusedTuning tune = fused_tuning();
+  unsigned long long total = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    GridView g = t->view();
+    RQ_CUDA(cudaMemsetAsync(res->cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    {
+      PhaseScope p2(ctx, "range_fill");
+#define RQ_FUSED(QN_, NW_)                                                                                         \
+  launch_fused<D, QN_, NW_>(ctx, g, dq, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p,  \
+                            want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,               \
+                            count_only ? 0 : 1)
+      if (tune.qn == 1) {
+        if (tune.nw == 8) RQ_FUSED(1, 8); else if (tune.nw == 24) RQ_FUSED(1, 24); else RQ_FUSED(1, 16);
+      } else {
+        if (tune.nw == 8) RQ_FUSED(2, 8); else if (tune.nw == 24) RQ_FUSED(2, 24); else RQ_FUSED(2, 16);
+      }
+#undef RQ_FUSED
+    }
+    RQ_CUDA(cudaMemcpyAsync(&total, res->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+    if (count_only || total <= cap) break;
+    RQ_REQUIRE(attempt == 0, "internal: range output did not fit after resizing");
+    cap = (size_t)total + (size_t)(total / 32) + 1024;
+    res->idx.ensure(cap, st, 0, 1.0);
+    if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
+    cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
+  }
+  res->n_queries = nq;
+  res->total = (int64_t)total;
+  res->has_lists = !count_only;
+  res->has_dist = !count_only && want_dist;
+}

@@ -59,8 +59,8 @@ struct rrtqx_tree {
   rrtqx::WrapInfo wrap{};
   int64_t n = 0;         // tree size
   int64_t n_sorted = 0;  // covered by the grid index
-  double occupancy = 8.0;
-  double aspect = 4.0;   // cell width across rows / cell length along x
+  double occupancy = 4.0;
+  double aspect = 1.0;   // cell width across rows / cell length along x
   int64_t tail_limit = 4096;
 
   // node table (insertion order)

@@ -18,7 +18,8 @@ def ctx():
     from rrtqx_3d_b200.device import Context
     c = Context(0)
     yield c
-    c.close()
+    # not closed explicitly: trees / results created by the tests may outlive this fixture until
+    # they are garbage collected, and each of them keeps the context alive through a reference
 
 
 @pytest.fixture(scope="session")
