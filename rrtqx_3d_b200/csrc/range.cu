@@ -22,17 +22,20 @@ namespace rrtqx {
 // time share one compact candidate region (L1 reuse), and the two queries of a
 // group have almost identical candidate rows.
 template <int D>
-__global__ void query_key_kernel(GridView g, int S, int nsx, int nsy, const double *__restrict__ q, int64_t nq,
+__global__ void query_key_kernel(GridView g, int S, int F, int nsx, int nsy, const double *__restrict__ q, int64_t nq,
                                  int32_t *__restrict__ key, int32_t *__restrict__ hist) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   const double *r = q + i * D;
-  int cx = cell_of(r[0], g.lo[0], g.inv[0], g.nx);
-  int cy = cell_of(r[1], g.lo[1], g.inv[1], g.ny);
-  int cz = D >= 3 ? cell_of(r[2], g.lo[2], g.inv[2], g.nz) : 0;
-  int sc = ((cz / S) * nsy + cy / S) * nsx + cx / S;
-  int local = ((cz % S) * S + cy % S) * S + cx % S;
-  int c = sc * (S * S * S) + local;
+  // sub-cell coordinates: F sub-cells per grid cell and direction
+  const double f = (double)F;
+  int cx = cell_of(r[0], g.lo[0], g.inv[0] * f, g.nx * F);
+  int cy = cell_of(r[1], g.lo[1], g.inv[1] * f, g.ny * F);
+  int cz = D >= 3 ? cell_of(r[2], g.lo[2], g.inv[2] * f, g.nz * F) : 0;
+  const int SF = S * F;
+  int sc = ((cz / SF) * nsy + cy / SF) * nsx + cx / SF;
+  int local = ((cz % SF) * SF + cy % SF) * SF + cx % SF;
+  int c = sc * (SF * SF * SF) + local;
   key[i] = c;
   atomicAdd(&hist[c], 1);
 }
@@ -59,8 +62,9 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   const int TB = 256;
   r->qorder.ensure((size_t)nq, st);
   static int S = [] { const char *e = getenv("RRTQX_QSORT_S"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+  static int F = [] { const char *e = getenv("RRTQX_QSORT_F"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   const int nsx = (t->nx + S - 1) / S, nsy = (t->ny + S - 1) / S, nsz = (t->nz + S - 1) / S;
-  const int64_t nbins = (int64_t)nsx * nsy * nsz * S * S * S;
+  const int64_t nbins = (int64_t)nsx * nsy * nsz * S * S * S * F * F * F;
   if (t->n_sorted == 0 || nq < 2048 || nbins > (int64_t)(1 << 28)) {
     iota_kernel<<<div_up(nq, TB), TB, 0, st>>>(r->qorder.p, nq);
     post_launch(ctx);
@@ -72,7 +76,7 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   r->qstart.ensure((size_t)ncell + 1, st);
   RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   GridView g = t->view();
-  query_key_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(g, S, nsx, nsy, dq, nq, r->qkey.p, r->qhist.p);
+  query_key_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(g, S, F, nsx, nsy, dq, nq, r->qkey.p, r->qhist.p);
   post_launch(ctx);
   exclusive_scan<int32_t, int32_t>(ctx, r->qhist.p, ncell, r->qstart.p, r->scan_tmp32);
   RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
