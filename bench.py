@@ -39,6 +39,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/range_traffic.json, written by hand from the `ncu --set full` report of the C2 run)."""
+    p = os.path.join(ROOT, "profiles", "range_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -53,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,7 +105,7 @@ def cpu_range_baseline(pts, qs, r, seconds_target=12.0, nthreads=None):
     tree = oracle.KDTree(3)
     tree.insert_batch(pts)
     build_s = time.perf_counter() - t0
-    probe = min(len(qs), 2000 * nthreads)
+    probe = min(len(qs), 64 * nthreads)
     t0 = time.perf_counter()
     tree.range_batch(r, qs[:probe], want_lists=True, nthreads=nthreads)
     dt = time.perf_counter() - t0
@@ -119,12 +129,12 @@ def run_reference(args, rank, world):
     import oracle
     tree = oracle.KDTree(3)
     tree.insert_batch(pts)
-    probe = min(len(qs), 1000 * nthreads)
+    probe = min(len(qs), 64 * nthreads)
     t0 = time.perf_counter()
     tree.range_batch(r, qs[:probe], nthreads=nthreads)
     rate = probe / (time.perf_counter() - t0)
-    budget_s = 90.0 / max(1, args.steps + args.warmup)       # whole run within a few minutes
-    sample = int(min(len(qs), max(1000, rate * min(budget_s, 15.0))))
+    budget_s = 120.0 / max(1, args.steps + args.warmup)      # whole run within a few minutes
+    sample = int(min(len(qs), max(nthreads, rate * min(budget_s, 15.0))))
     times = []
     for it in range(args.warmup + args.steps):
         lo = (it * sample) % max(1, len(qs) - sample + 1)
@@ -171,7 +181,7 @@ def build_c3_edges(tree, pts, r_edge):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nodes", type=int, default=1_000_000)
@@ -234,15 +244,16 @@ def main():
         h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(p), False), "version": 3}
         return torch_mod.as_tensor(h, device="cuda")
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         total = step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.rows.clear()            # keep only samples taken during the timed region
     launches0 = ctx.kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern = {"range_sort": [], "range_count": [], "range_scan": [], "range_fill": []}
     torch.cuda.synchronize()
@@ -283,9 +294,9 @@ def main():
     achieved = alg_bytes / (ms_local / 1e3) / 1e9
     fill_share = kern_ms["range_fill"] / ms_local
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                "traffic": ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
                 "note": "achieved = compulsory bytes of the whole range-query step / CUDA-event time of the step "
-                        "(sort+count+scan+fill); dominant kernel = range_query_kernel<3,FILL>",
+                        "(query sort + fused single-pass kernel); dominant kernel = range_fused_kernel<3,2,24>",
                 "kernel_ms": kern_ms, "dominant_kernel_share": fill_share,
                 "dominant_kernel_frac": alg_bytes / (kern_ms["range_fill"] / 1e3) / 1e9 / peak_gbs}
 
