@@ -306,6 +306,45 @@ RRTQX_API rrtqx_status rrtqx_sweep_result_flags(rrtqx_sweep_result *r,
                                                 uint8_t *edge_flag,
                                                 uint8_t *node_flag);
 
+/* ------------------------------------------- 2-D polygon world (DubinsEdge) */
+/* Obstacle kinds 1 (ball) and 3 (polygon) of the Otte generation
+ * (DRRT_data_structures.jl:135-265) flattened: kind[n], centres n x 2 and
+ * radii n of the bounding circles (for polygons: bbox midpoint / farthest
+ * vertex, :229-241, computed by the caller exactly as the constructor does),
+ * active[n] = !(obstacleUnused || lifeSpan <= 0), polygon vertices as CSR
+ * (vert_ptr[n+1] host array, verts nv x 2). */
+RRTQX_API rrtqx_status rrtqx_polygons_create(rrtqx_ctx *ctx,
+                                             rrtqx_polygons **out);
+RRTQX_API rrtqx_status rrtqx_polygons_destroy(rrtqx_polygons *p);
+RRTQX_API rrtqx_status rrtqx_polygons_upload(rrtqx_polygons *p,
+                                             const int32_t *kind,
+                                             const double *centers,
+                                             const double *radii,
+                                             const uint8_t *active,
+                                             const int64_t *vert_ptr,
+                                             const double *verts, int64_t n);
+/* explicitEdgeCheck2D (DRRT.jl:1523-1578, via distanceSqrdPointToSegment
+ * :1060-1083 and segmentDistSqrd :1144-1202) OR-ed over the obstacle list
+ * (explicitEdgeCheck(C,edge) DRRT.jl:1660-1678) for n segments given by
+ * starts/ends (n x 2) and the robot radius `radius`. */
+RRTQX_API rrtqx_status rrtqx_segment_check_2d_batch(rrtqx_polygons *p,
+                                                    const double *starts,
+                                                    const double *ends,
+                                                    int64_t n, double radius,
+                                                    uint32_t flags,
+                                                    uint8_t *collide_out);
+/* Dubins explicitEdgeCheck(S, edge, ob) (DRRT_DubinsEdge_functions.jl:750-774)
+ * OR-ed over the obstacle list: coarse start->end segment test with radius
+ * robot_radius + 2*min_turn_radius, then every consecutive pair of trajectory
+ * points with robot_radius.  Trajectories (edge.trajectory[:,1:2]) are a CSR:
+ * traj_ptr[n_edges+1], traj_xy npts x 2.  Collision booleans are bit-exact
+ * GIVEN the trajectory points. */
+RRTQX_API rrtqx_status rrtqx_dubins_edge_check_batch(
+    rrtqx_polygons *p, const double *starts, const double *ends,
+    const int64_t *traj_ptr, const double *traj_xy, int64_t n_edges,
+    double robot_radius, double min_turn_radius, uint32_t flags,
+    uint8_t *collide_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,11 @@ SIGNATURES = {
     "rrtqx_sweep_result_sizes": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "rrtqx_sweep_result_fetch": (i32, [vp, vp, vp]),
     "rrtqx_sweep_result_flags": (i32, [vp, vp, vp]),
+    "rrtqx_polygons_create": (i32, [vp, C.POINTER(vp)]),
+    "rrtqx_polygons_destroy": (i32, [vp]),
+    "rrtqx_polygons_upload": (i32, [vp, vp, vp, vp, vp, vp, vp, i64]),
+    "rrtqx_segment_check_2d_batch": (i32, [vp, vp, vp, i64, f64, u32, vp]),
+    "rrtqx_dubins_edge_check_batch": (i32, [vp, vp, vp, vp, vp, i64, f64, f64, u32, vp]),
 }
 
 _lib = None

@@ -355,3 +355,83 @@ class EdgeSet:
                                                    other_ids.size, A.ptr(inf), float(robot_radius), float(delta),
                                                    int(flags), C.byref(result.h)), self.ctx.h)
         return result
+
+
+class PolygonSet:
+    """rrtqx_polygons: the 2-D obstacle list of the Otte generation (kinds 1 = ball, 3 = polygon)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.L = ctx.L
+        h = A.vp()
+        A.check(self.L.rrtqx_polygons_create(ctx.h, C.byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_polygons_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def polygon_bound(poly):
+        """Bounding circle exactly as the Obstacle(kind, polygon) constructor computes it
+        (DRRT_data_structures.jl:229-241): bbox midpoint, radius = sqrt(max_i |v_i - c|^2)."""
+        poly = np.asarray(poly, dtype=np.float64).reshape(-1, 2)
+        cx = (poly[:, 0].max() + poly[:, 0].min()) / 2.0
+        cy = (poly[:, 1].max() + poly[:, 1].min()) / 2.0
+        dx, dy = poly[:, 0] - cx, poly[:, 1] - cy
+        return cx, cy, float(np.sqrt((dx * dx + dy * dy).max()))
+
+    def upload(self, obstacles, active=None):
+        """obstacles: list of ("ball", (cx, cy), r) or ("polygon", vertices Px2)."""
+        n = len(obstacles)
+        kind = np.zeros(n, dtype=np.int32)
+        centers = np.zeros((n, 2))
+        radii = np.zeros(n)
+        vptr = np.zeros(n + 1, dtype=np.int64)
+        verts = []
+        for i, ob in enumerate(obstacles):
+            if ob[0] == "ball":
+                kind[i] = 1
+                centers[i] = ob[1]
+                radii[i] = ob[2]
+            else:
+                kind[i] = 3
+                v = np.asarray(ob[1], dtype=np.float64).reshape(-1, 2)
+                centers[i, 0], centers[i, 1], radii[i] = self.polygon_bound(v)
+                verts.append(v)
+            vptr[i + 1] = vptr[i] + (len(verts[-1]) if kind[i] == 3 else 0)
+        vv = np.ascontiguousarray(np.concatenate(verts, axis=0)) if verts else np.zeros((0, 2))
+        act = None if active is None else A.as_u8(np.asarray(active).astype(np.uint8))
+        A.check(self.L.rrtqx_polygons_upload(self.h, A.ptr(kind), A.ptr(centers), A.ptr(radii), A.ptr(act), A.ptr(vptr),
+                                             A.ptr(vv) if len(vv) else None, n), self.ctx.h)
+        self.kind, self.centers, self.radii, self.vptr, self.verts = kind, centers, radii, vptr, vv
+
+
+def segment_check_2d_batch(polys: PolygonSet, starts, ends, radius, flags=0):
+    """explicitEdgeCheck2D OR-ed over the obstacle list for n 2-D segments."""
+    starts, ends = A.as_f64(starts, 2), A.as_f64(ends, 2)
+    n = starts.shape[0]
+    out = np.empty(n, dtype=np.uint8)
+    A.check(polys.L.rrtqx_segment_check_2d_batch(polys.h, A.ptr(starts), A.ptr(ends), n, float(radius), int(flags),
+                                                 A.ptr(out)), polys.ctx.h)
+    return out
+
+
+def dubins_edge_check_batch(polys: PolygonSet, starts, ends, traj_ptr, traj_xy, robot_radius, min_turn_radius, flags=0):
+    """Dubins explicitEdgeCheck OR-ed over the obstacle list; trajectories as CSR (traj_ptr, traj_xy)."""
+    starts, ends = A.as_f64(starts, 2), A.as_f64(ends, 2)
+    traj_ptr = np.ascontiguousarray(traj_ptr, dtype=np.int64)
+    traj_xy = A.as_f64(traj_xy, 2)
+    n = starts.shape[0]
+    out = np.empty(n, dtype=np.uint8)
+    A.check(polys.L.rrtqx_dubins_edge_check_batch(polys.h, A.ptr(starts), A.ptr(ends), A.ptr(traj_ptr),
+                                                  A.ptr(traj_xy) if len(traj_xy) else None, n, float(robot_radius),
+                                                  float(min_turn_radius), int(flags), A.ptr(out)), polys.ctx.h)
+    return out

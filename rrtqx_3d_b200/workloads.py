@@ -105,3 +105,63 @@ def building2_spheres():
                         "building2_spheres.csv")
     rows = np.loadtxt(path, delimiter=",", comments="#")
     return np.ascontiguousarray(rows[:, 0:3]), np.ascontiguousarray(rows[:, 3]), rows[:, 4].astype(np.int32)
+
+
+# ------------------------------------------------------------ config C4 (Dubins, 2-D polygon world)
+def c4_city_blocks(n_side: int = 10, half: float = 3.0, pitch: float = 10.0, first: float = -45.0):
+    """10 x 10 grid of 6 x 6 square city blocks centred at (first + pitch*i, first + pitch*j), as kind-3 polygons."""
+    obs = []
+    for j in range(n_side):
+        for i in range(n_side):
+            cx, cy = first + pitch * i, first + pitch * j
+            obs.append(("polygon", np.array([[cx - half, cy - half], [cx + half, cy - half], [cx + half, cy + half],
+                                             [cx - half, cy + half]])))
+    return obs
+
+
+def arc_line_arc_trajectory(start, end, r_turn: float, step: float = 0.1):
+    """A Dubins-shaped polyline (left arc, straight, left arc) from pose `start` (x, y, theta) towards `end`,
+    arcs sampled every `step` rad like the reference's collect(phi_start:0.1:phi_end)
+    (DRRT_DubinsEdge_functions.jl:506-655).  Synthetic workload generator -- NOT the reference's solver; the
+    GPU check is bit-exact given the trajectory points, whatever produced them."""
+    x0, y0, th0 = start
+    x1, y1, th1 = end
+    pts = [(x0, y0)]
+    c0 = (x0 - r_turn * math.sin(th0), y0 + r_turn * math.cos(th0))          # left-turn circle at start
+    c1 = (x1 - r_turn * math.sin(th1), y1 + r_turn * math.cos(th1))          # left-turn circle at end
+    hdg = math.atan2(c1[1] - c0[1], c1[0] - c0[0])                            # LSL: tangent heading
+    a0 = (hdg - th0) % (2 * math.pi)
+    k = 1
+    while k * step < a0:
+        a = th0 + k * step
+        pts.append((c0[0] + r_turn * math.sin(a), c0[1] - r_turn * math.cos(a)))
+        k += 1
+    pts.append((c0[0] + r_turn * math.sin(hdg), c0[1] - r_turn * math.cos(hdg)))
+    pts.append((c1[0] + r_turn * math.sin(hdg), c1[1] - r_turn * math.cos(hdg)))
+    a1 = (th1 - hdg) % (2 * math.pi)
+    k = 1
+    while k * step < a1:
+        a = hdg + k * step
+        pts.append((c1[0] + r_turn * math.sin(a), c1[1] - r_turn * math.cos(a)))
+        k += 1
+    pts.append((x1, y1))
+    return np.asarray(pts, dtype=np.float64)
+
+
+def c4_workload(n_nodes: int = 200_000, n_edges: int = 100_000, r_edge: float = 4.0, r_turn: float = 1.0, seed: int = 4):
+    """Config C4 pieces: nodes uniform in [-50,50]^2 x {0} x [0,2pi) (dubinsExperimentsForPaper.jl:77-78), random
+    directed edges of length <= r_edge with arc-line-arc trajectories (CSR)."""
+    lo, hi = [-50.0, -50.0, 0.0, 0.0], [50.0, 50.0, 0.0, 2.0 * math.pi]
+    nodes = uniform_points(seed, n_nodes, lo, hi)
+    u = uniform01(seed + 1, 0, 4 * n_edges).reshape(n_edges, 4)
+    src = (u[:, 0] * n_nodes).astype(np.int64)
+    ang, rad = 2 * math.pi * u[:, 1], r_edge * np.sqrt(u[:, 2])
+    starts = nodes[src][:, [0, 1, 3]]
+    ends = np.stack([starts[:, 0] + rad * np.cos(ang), starts[:, 1] + rad * np.sin(ang), 2 * math.pi * u[:, 3]], axis=1)
+    ptr = np.zeros(n_edges + 1, dtype=np.int64)
+    chunks = []
+    for e in range(n_edges):
+        t = arc_line_arc_trajectory(starts[e], ends[e], r_turn)
+        chunks.append(t)
+        ptr[e + 1] = ptr[e] + len(t)
+    return nodes, starts, ends, ptr, np.concatenate(chunks, axis=0)

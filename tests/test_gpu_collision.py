@@ -174,3 +174,64 @@ def test_obstacle_add_and_remove_sweep(ctx):
     # QX semantics (obstacle disabled before the loop, DRRT_Q.jl:3301-3302): nothing restored
     rq = E.remove_sweep(S, 0, others, inf, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_REMOVED_INACTIVE)
     assert rq.sizes()[0] == 0 and rq.sizes()[1] == 0
+
+
+def _orc_obstacles_2d(polyset):
+    obs = []
+    for i in range(len(polyset.kind)):
+        ob = oracle.Obstacle2D()
+        ob.kind = int(polyset.kind[i])
+        ob.pos[0], ob.pos[1] = polyset.centers[i]
+        ob.radius = polyset.radii[i]
+        ob.life_span = float("inf")
+        ob.unused = 0
+        if ob.kind == 3:
+            v = np.ascontiguousarray(polyset.verts[polyset.vptr[i]:polyset.vptr[i + 1]])
+            ob.n_vert = len(v)
+            ob._keep = v
+            ob.poly = oracle._p(v, oracle.c_f64p)
+        obs.append(ob)
+    return obs
+
+
+def test_polygon_world_segment_and_dubins_checks(ctx):
+    """DRRT.jl:1523-1578 + DRRT_DubinsEdge_functions.jl:750-774 against the oracle, bit-exact booleans."""
+    from rrtqx_3d_b200.device import PolygonSet, dubins_edge_check_batch, segment_check_2d_batch
+    obstacles = W.c4_city_blocks()[:40]
+    obstacles += [("ball", (5.0, 5.0), 2.0), ("ball", (-20.0, 31.0), 4.0),
+                  ("polygon", np.array([[0.0, 0.0], [3.0, 0.5], [1.0, 4.0]])),          # triangle
+                  ("polygon", np.array([[30.0, 30.0], [30.0, 36.0]]))]                   # degenerate 2-vertex polygon
+    P = PolygonSet(ctx)
+    P.upload(obstacles)
+    orc = _orc_obstacles_2d(P)
+    L = oracle.lib()
+    f = lambda a: oracle._p(np.ascontiguousarray(a, dtype=np.float64), oracle.c_f64p)
+    n = 20000
+    starts = W.uniform_points(61, n, [-50.0, -50.0], [50.0, 50.0])
+    ends = starts + W.uniform_points(62, n, [-4.0, -4.0], [4.0, 4.0])
+    ends[::9, 0] = starts[::9, 0]                  # exactly vertical segments (the 1e-6 branch of segmentDistSqrd)
+    ends[::11] = starts[::11]                      # zero-length segments
+    rad = 0.5
+    got = segment_check_2d_batch(P, starts, ends, rad)
+    want = np.zeros(n, dtype=np.uint8)
+    import ctypes as C
+    for i in range(n):
+        for ob in orc:
+            if L.orc_edge_check_2d(C.byref(ob), f(starts[i]), f(ends[i]), rad):
+                want[i] = 1
+                break
+    assert np.array_equal(got, want) and 0.05 < want.mean() < 0.9
+    # Dubins edges with arc-line-arc trajectories
+    nodes, s3, e3, ptr, traj = W.c4_workload(5000, 3000)
+    got = dubins_edge_check_batch(P, s3[:, :2], e3[:, :2], ptr, traj, 0.5, 1.0)
+    want = np.zeros(len(s3), dtype=np.uint8)
+    for i in range(len(s3)):
+        t = np.ascontiguousarray(traj[ptr[i]:ptr[i + 1]])
+        for ob in orc:
+            if L.orc_edge_check_dubins(C.byref(ob), f(s3[i, :2]), f(e3[i, :2]), f(t), len(t), 0.5, 1.0):
+                want[i] = 1
+                break
+    assert np.array_equal(got, want) and 0.05 < want.mean() < 0.95
+    # inactive obstacles are skipped
+    P.upload(obstacles, active=np.zeros(len(obstacles)))
+    assert not segment_check_2d_batch(P, starts, ends, rad).any()
