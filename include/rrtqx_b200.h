@@ -242,6 +242,24 @@ RRTQX_API rrtqx_status rrtqx_node_check_batch(rrtqx_ctx *ctx,
                                               uint8_t *collide_out,
                                               double *cert_out);
 
+/* The planner's per-iteration geometric work in ONE launch (rrtqx.jl:926-950,
+ * extend() DRRT_Q.jl:2546-2641) for the new sample `point` (d doubles, host):
+ *   kdFindNearest            -> nearest_idx / nearest_dist
+ *   explicitNodeCheck(3D)    -> point_collides / point_cert (RRTQX_CHECK_QUICK_PASS selects :1520 vs :1558)
+ *   kdFindWithinRange(range) -> *n_neighbors, nbr_idx[], nbr_dist[] (JList keys)
+ *   explicitEdgeCheck of edge(new -> n) and edge(n -> new) for every neighbour n
+ *                            -> fwd_collide[], rev_collide[]  (the test is not symmetric)
+ * `capacity` = length of the four neighbour arrays; *n_neighbors receives the
+ * full count (if it exceeds capacity only the first `capacity` are written).
+ * At most 768 obstacles; d == 3 for the edge checks (other d: flags are 0).
+ * Results arrive through mapped pinned memory: one launch, one synchronise. */
+RRTQX_API rrtqx_status rrtqx_extend_query(
+    rrtqx_tree *tree, const rrtqx_spheres *spheres, const double *point,
+    double range, double robot_radius, uint32_t flags, int32_t capacity,
+    int32_t *nearest_idx, double *nearest_dist, uint8_t *point_collides,
+    double *point_cert, int32_t *n_neighbors, int32_t *nbr_idx,
+    double *nbr_dist, uint8_t *fwd_collide, uint8_t *rev_collide);
+
 /* ------------------------------------------------- resident edge set + sweeps */
 /* Device mirror of the planner's out-edge lists: for node v the reference
  * iterates InitialNeighborListOut then rrtNeighborsOut

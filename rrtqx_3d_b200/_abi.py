@@ -49,6 +49,8 @@ SIGNATURES = {
     "rrtqx_range_result_fetch": (i32, [vp, vp, vp]),
     "rrtqx_range_result_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "rrtqx_nearest_batch": (i32, [vp, vp, i64, vp, vp]),
+    "rrtqx_extend_query": (i32, [vp, vp, vp, f64, f64, u32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(C.c_uint8),
+                                 C.POINTER(f64), C.POINTER(i32), vp, vp, vp, vp]),
     "rrtqx_spheres_create": (i32, [vp, C.POINTER(vp)]),
     "rrtqx_spheres_destroy": (i32, [vp]),
     "rrtqx_spheres_upload": (i32, [vp, vp, vp, vp, i64]),

@@ -147,6 +147,7 @@ rrtqx_status rrtqx_tree_destroy(rrtqx_tree *tree) {
       auto it = g_nearest_scratch.find(tree);
       if (it != g_nearest_scratch.end()) { delete it->second; g_nearest_scratch.erase(it); }
     }
+    extend_state_drop(tree);
     delete tree;
   });
 }
@@ -341,6 +342,20 @@ rrtqx_status rrtqx_nearest_batch(rrtqx_tree *tree, const double *queries, int64_
       h->sortbuf.ctx = ctx;
     }
     nearest_query(tree, &h->sortbuf, queries, n_queries, idx_out, dist_out, h->idx, h->dist);
+  });
+}
+
+rrtqx_status rrtqx_extend_query(rrtqx_tree *tree, const rrtqx_spheres *spheres, const double *point, double range,
+                                double robot_radius, uint32_t flags, int32_t capacity, int32_t *nearest_idx,
+                                double *nearest_dist, uint8_t *point_collides, double *point_cert,
+                                int32_t *n_neighbors, int32_t *nbr_idx, double *nbr_dist, uint8_t *fwd_collide,
+                                uint8_t *rev_collide) {
+  if (!tree || !spheres) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    extend_query(tree, spheres, point, range, robot_radius, flags, capacity, nearest_idx, nearest_dist, point_collides,
+                 point_cert, n_neighbors, nbr_idx, nbr_dist, fwd_collide, rev_collide);
   });
 }
 

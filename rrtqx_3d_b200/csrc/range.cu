@@ -313,6 +313,7 @@ static void launch_range(rrtqx_tree *t, bool fill, const double *dq, const int32
 
 
 #include "range_fused.cuh"
+#include "extend.cuh"
 
 template <int D>
 static void range_query_impl(rrtqx_tree *t, const double *queries, int64_t nq, double r, const double *ranges,

@@ -357,6 +357,29 @@ class EdgeSet:
         return result
 
 
+class ExtendResult:
+    """Outputs of one rrtqx_extend_query call."""
+    __slots__ = ("nearest_idx", "nearest_dist", "point_collides", "point_cert", "count", "idx", "dist", "fwd", "rev")
+
+
+def extend_query(tree: DeviceTree, spheres: SphereSet, point, r, robot_radius, flags=0, capacity=4096, bufs=None):
+    """One planner iteration's geometric work in one launch (rrtqx.jl:926-950, DRRT_Q.jl:2546-2641)."""
+    p = A.as_f64(point).reshape(-1)
+    if bufs is None or len(bufs[0]) < capacity:
+        bufs = (np.empty(capacity, dtype=np.int32), np.empty(capacity, dtype=np.float64),
+                np.empty(capacity, dtype=np.uint8), np.empty(capacity, dtype=np.uint8))
+    ni, nd, pc, ce, cnt = A.i32(0), A.f64(0.0), C.c_uint8(0), A.f64(0.0), A.i32(0)
+    A.check(tree.L.rrtqx_extend_query(tree.h, spheres.h, A.ptr(p), float(r), float(robot_radius), int(flags), int(capacity),
+                                      C.byref(ni), C.byref(nd), C.byref(pc), C.byref(ce), C.byref(cnt), A.ptr(bufs[0]),
+                                      A.ptr(bufs[1]), A.ptr(bufs[2]), A.ptr(bufs[3])), tree.ctx.h)
+    out = ExtendResult()
+    out.nearest_idx, out.nearest_dist = int(ni.value), float(nd.value)
+    out.point_collides, out.point_cert, out.count = bool(pc.value), float(ce.value), int(cnt.value)
+    m = min(out.count, capacity)
+    out.idx, out.dist, out.fwd, out.rev = bufs[0][:m], bufs[1][:m], bufs[2][:m], bufs[3][:m]
+    return out
+
+
 class PolygonSet:
     """rrtqx_polygons: the 2-D obstacle list of the Otte generation (kinds 1 = ball, 3 = polygon)."""
 
