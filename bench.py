@@ -178,6 +178,77 @@ def build_c3_edges(tree, pts, r_edge):
     return src, dst, parent
 
 
+def c1_replay(ctx, n_iter):
+    """Config C1: planner-style incremental loop (one sample per iteration) through rrtqx_extend_query +
+    rrtqx_tree_insert on the GPU, and the same geometric work through the oracle on the CPU (every 25th
+    iteration timed, trees kept identical)."""
+    import ctypes as C
+
+    import oracle
+    from rrtqx_3d_b200 import _abi as A
+    from rrtqx_3d_b200.device import DeviceTree, SphereSet, extend_query
+    centers, radii, _ = W.building2_spheres()
+    S = SphereSet(ctx, centers, radii)
+    samples = W.uniform_points(1, n_iter, [-W.ENV_RAD] * 3, [W.ENV_RAD] * 3)
+    goal = np.array([4.0, 16.5, -7.5])
+    t = DeviceTree(ctx, 3)
+    t.insert(goal)
+    accept = np.zeros(n_iter, dtype=bool)
+    bufs = (np.empty(8192, np.int32), np.empty(8192, np.float64), np.empty(8192, np.uint8), np.empty(8192, np.uint8))
+    n = 1
+    nbrs = 0
+    t0 = time.perf_counter()
+    for it in range(n_iter):
+        r = W.shrinking_ball_radius(n, 3, W.DELTA, W.BALL_CONSTANT)
+        res = extend_query(t, S, samples[it], r, W.ROBOT_RADIUS, A.CHECK_QUICK_PASS, capacity=8192, bufs=bufs)
+        nbrs += res.count
+        if not res.point_collides:
+            t.insert(samples[it])
+            accept[it] = True
+            n += 1
+    gpu_s = time.perf_counter() - t0
+    # CPU: same sequence, geometric work of every 25th iteration timed
+    L = oracle.lib()
+    sph, ns = oracle.make_spheres(centers, radii)
+    orc = oracle.KDTree(3)
+    orc.insert(goal)
+    P = lambda a: oracle._p(np.ascontiguousarray(a, dtype=np.float64), oracle.c_f64p)
+    cpu_s, cpu_n = 0.0, 0
+    c = C.c_double()
+    for it in range(n_iter):
+        if it % 25 == 0:
+            p = samples[it]
+            pos = None
+            t1 = time.perf_counter()
+            r = W.shrinking_ball_radius(len(orc), 3, W.DELTA, W.BALL_CONSTANT)
+            orc.find_nearest(p)
+            L.orc_point_check(sph, ns, 0, P(p), W.ROBOT_RADIUS, C.byref(c))
+            idx, key = orc.find_within_range(r, p)
+            orc.empty(idx)
+            k = len(idx)
+            if k:
+                src = np.full(2 * k, len(orc), dtype=np.int32)       # virtual node index of the new sample
+                dst = np.concatenate([idx, idx]).astype(np.int32)
+                src[k:], dst[k:] = idx, len(orc)
+                ptr = L.orc_kd_positions
+                ptr.restype = C.POINTER(C.c_double)
+                ptr.argtypes = [C.c_void_p]
+                pos = np.concatenate([np.ctypeslib.as_array(ptr(orc.h), shape=(len(orc), 3)), p.reshape(1, 3)])
+                out = np.zeros(2 * k, dtype=np.uint8)
+                L.orc_edge_check_batch(sph, ns, P(pos), 3, oracle._p(src, oracle.c_i32p), oracle._p(dst, oracle.c_i32p), 0,
+                                       2 * k, W.ROBOT_RADIUS, 0, oracle._p(out, oracle.c_u8p), 1)
+            cpu_s += time.perf_counter() - t1
+            cpu_n += 1
+        if accept[it]:
+            orc.insert(samples[it])
+    return {"workload": "C1 RRTx SimpleEdge 3-D replay: per iteration nearest + node check + range(r(n)) + 2k edge checks "
+                        "(31 building2 spheres) + insert",
+            "iterations": n_iter, "nodes_final": n, "mean_neighbours": nbrs / n_iter,
+            "gpu_us_per_iteration": 1e6 * gpu_s / n_iter, "cpu_us_per_iteration": 1e6 * cpu_s / max(cpu_n, 1),
+            "cpu": "oracle, 1 thread (the reference planner is single-threaded), every 25th iteration timed",
+            "note": "latency-bound: one launch + one stream synchronise per iteration, results via mapped pinned memory"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +262,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-c1", action="store_true")
+    ap.add_argument("--c1-iterations", type=int, default=20000)
     ap.add_argument("--sweep-edge-radius", type=float, default=0.5346)
     ap.add_argument("--sweep-obstacles", type=int, default=256)
     args = ap.parse_args()
@@ -381,6 +454,12 @@ def main():
                                   "algorithmic_bytes": sbytes, "hbm_frac": sbytes / (sms / 1e3) / 1e9 / peak_gbs}
         except Exception as exc:  # the headline line must still be printed
             line["edge_sweep"] = {"error": repr(exc)}
+
+    if not args.no_c1 and rank == 0 and world == 1:
+        try:
+            line["planner_iteration"] = c1_replay(ctx, args.c1_iterations)
+        except Exception as exc:
+            line["planner_iteration"] = {"error": repr(exc)}
 
     # ---------------------------------------------------------- CPU baseline
     if not args.no_cpu and rank == 0 and world == 1:
