@@ -65,11 +65,13 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   static int F = [] { const char *e = getenv("RRTQX_QSORT_F"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   const int nsx = (t->nx + S - 1) / S, nsy = (t->ny + S - 1) / S, nsz = (t->nz + S - 1) / S;
   const int64_t nbins = (int64_t)nsx * nsy * nsz * S * S * S * F * F * F;
+  r->qbins = 0;
   if (t->n_sorted == 0 || nq < 2048 || nbins > (int64_t)(1 << 28)) {
     iota_kernel<<<div_up(nq, TB), TB, 0, st>>>(r->qorder.p, nq);
     post_launch(ctx);
     return;
   }
+  r->qbins = nbins;
   const int ncell = (int)nbins;
   r->qkey.ensure((size_t)nq, st);
   r->qhist.ensure((size_t)ncell + 1, st);

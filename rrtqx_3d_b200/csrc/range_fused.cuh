@@ -1,24 +1,30 @@
 // range_fused.cuh -- single-pass batched kdFindWithinRange (included by range.cu,
 // inside namespace rrtqx).
 //
-// One warp per group of QN consecutive (cell-sorted) queries:
+// One warp per group of QN = 2 consecutive (cell-sorted) queries:
 //   * the candidate region is the set of grid rows (runs of cells along x)
 //     that can hold a point within r; it is computed conservatively in FP32
 //     cell units (margins far above the rounding error), never deciding a
 //     result -- membership is always the exact FP64 test s < T_lt(r);
-//   * rows are short (fine cells give tight culling), so a warp works on
-//     32/W rows at once: W-lane sub-groups each walk one row;
-//   * every candidate is loaded once and tested against all QN queries;
+//   * rows are short (fine cells give tight culling), so they are flattened
+//     into a shared-memory table of "octets" (start slot, 1..8 valid points)
+//     and each 8-lane sub-group takes one octet per trip: every sub-group is
+//     busy whatever the row lengths are; 4 trips of loads are in flight before
+//     the first test;
+//   * candidates are read from the SoA arrays (an octet = one contiguous 64-byte run per coordinate);
+//   * every candidate is loaded once and tested against both queries;
 //   * hits are recorded as slot numbers in a per-warp shared-memory buffer;
 //     when the scan ends the warp reserves the exact output range with ONE
 //     atomic on a global cursor and flushes densely: coalesced 32-wide
 //     stores, sqrt evaluated on hits only with all lanes busy.
-// The tree is traversed once (no count pass).  Blocks own chunks of
-// consecutive sorted queries so their warps share candidate rows in L1.
+// The tree is traversed once (no count pass).  Blocks own chunks of consecutive
+// sorted queries (supercell-major order) so their warps share candidate rows in L1.
 
-constexpr int FUSED_CAP = 576;    // buffered hits per query before the direct-write fallback
-constexpr int FUSED_TAB = 256;    // octet-table entries per warp
-constexpr int FUSED_ROUNDS = 4;   // groups each warp takes from one block-level chunk
+constexpr int FUSED_TAB = 256;   // octet-table entries per warp
+constexpr int FUSED_ROUNDS = 4;  // groups each warp takes from one block-level chunk
+#ifndef FUSED_U
+#define FUSED_U 4
+#endif
 
 __device__ __forceinline__ void sts32(unsigned addr, int v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -39,7 +45,7 @@ __device__ __forceinline__ unsigned pin_reg(unsigned v) {
 template <int D, int QN>
 struct Group {
   double q[QN][D];
-  double T[QN];  // strict threshold on the radicand: hit <=> s < T
+  double T[QN];     // strict threshold on the radicand: hit <=> s < T
   float ff[QN][3];  // query position in (fractional) cell coordinates
   float r2f[QN];    // inflated r^2 (FP32, conservative)
   float rf[QN];     // inflated r
@@ -55,22 +61,24 @@ __device__ __forceinline__ int clampi(float v, int n) {  // floor + clamp to [0,
   return (int)fminf(fmaxf(floorf(v), 0.0f), (float)(n - 1));
 }
 
-// Conservative cell range [cxa, cxb] of row (cy,cz) that can hold a point
-// within r of the query; false if the row is out of reach.
+// Conservative cell range [cxa, cxb] of row (cy,cz) that can hold a point within r of the query at
+// ff (cell units); false if the row is out of reach.  (A single evaluation for the bounding box of
+// the group's queries was tried: sphere (+) box inflates the region by 30-60 % -- slower.)
 template <int D>
 __device__ __forceinline__ bool row_cells(const GridView &g, const FGrid &fg, const float *ff, float r2f, int cy, int cz,
                                           int &cxa, int &cxb) {
+  const float *fflo = ff, *ffhi = ff;
   // lower bounds of |p.y - q.y|, |p.z - q.z| in cell units; boundary rows also
   // hold the points clamped in from beyond the grid, so they give no bound on
   // that side.  1e-3 cells of slack covers the FP32 error of ff (coordinates
   // up to 1024 cells: ulp 6e-5) and the FP64 rounding of cell_of().
   const float ninf = -INFINITY;
-  float dyc = fmaxf(cy == 0 ? ninf : (float)cy - ff[1], cy == g.ny - 1 ? ninf : ff[1] - (float)(cy + 1));
+  float dyc = fmaxf(cy == 0 ? ninf : (float)cy - ffhi[1], cy == g.ny - 1 ? ninf : fflo[1] - (float)(cy + 1));
   dyc = fmaxf(dyc - 1e-3f, 0.0f);
   const float dy = dyc * fg.cell[1];
   float rem = r2f - dy * dy;
   if (D >= 3) {
-    float dzc = fmaxf(cz == 0 ? ninf : (float)cz - ff[2], cz == g.nz - 1 ? ninf : ff[2] - (float)(cz + 1));
+    float dzc = fmaxf(cz == 0 ? ninf : (float)cz - ffhi[2], cz == g.nz - 1 ? ninf : fflo[2] - (float)(cz + 1));
     dzc = fmaxf(dzc - 1e-3f, 0.0f);
     const float dz = dzc * fg.cell[2];
     rem -= dz * dz;
@@ -82,32 +90,39 @@ __device__ __forceinline__ bool row_cells(const GridView &g, const FGrid &fg, co
   }
   if (!(rem >= 0.0f)) return false;
   const float xc = sqrtf(rem) * (1.0f + 1e-5f) * fg.inv[0] + 1e-3f;
-  cxa = clampi(ff[0] - xc, g.nx);
-  cxb = clampi(ff[0] + xc, g.nx);
+  cxa = clampi(fflo[0] - xc, g.nx);
+  cxb = clampi(ffhi[0] + xc, g.nx);
   return true;
 }
 
+// candidate record of sorted slot j
+template <int D>
+struct Cand {
+  double x, y, z, w;
+};
+template <int D>
+__device__ __forceinline__ Cand<D> load_cand(const GridView &g, int j) {
+  Cand<D> c;
+  // SoA arrays: an octet is one contiguous 64-byte run per coordinate (fewest L1 wavefronts per trip)
+  c.x = g.sx[j];
+  c.y = g.sy[j];
+  c.z = D >= 3 ? g.sz[j] : 0.0;
+  c.w = D >= 4 ? g.sw[j] : 0.0;
+  return c;
+}
+
 // Scan all candidates of the group.  DIRECT = false: append hit slots to the
-// warp's shared buffer (up to FUSED_CAP per query), cnt[] = number of hits.
+// warp's shared buffer (up to CAP per query), cnt[] = number of hits.
 // DIRECT = true: write results at base[k] + ordinal (a query overflowed its
 // buffer).  Slots: j >= 0 is a position in the cell-sorted arrays, j < 0
 // encodes node -(j+1) of the unsorted tail.
-//
-// The candidate rows are short (fine cells), so they are flattened into a table
-// of "octets" (start slot, 1..8 valid points) in shared memory; each 8-lane
-// sub-group then takes one octet per trip, which keeps every sub-group busy
-// whatever the row lengths are.
-template <int D, int QN, bool DIRECT>
+template <int D, int QN, int CAP, bool DIRECT>
 __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, const Group<D, QN> &G, int lane,
                                            unsigned lt, unsigned sbuf, unsigned stab, int (&cnt)[QN],
                                            const int64_t (&base)[QN], int32_t *__restrict__ out_idx,
                                            double *__restrict__ out_dist) {
 #pragma unroll
   for (int k = 0; k < QN; ++k) cnt[k] = 0;
-  const double *__restrict__ sx = g.sx;
-  const double *__restrict__ sy = g.sy;
-  const double *__restrict__ sz = g.sz;
-  const double *__restrict__ sw = g.sw;
 
   auto visit = [&](bool valid, int slot, double px, double py, double pz, double pw) {
 #pragma unroll
@@ -122,7 +137,7 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
           if (out_dist) out_dist[base[k] + o] = __dsqrt_rn(s);
         }
       } else {
-        if (hit && o < FUSED_CAP) sts32(sbuf + 4u * (unsigned)(k * FUSED_CAP + o), slot);
+        if (hit && o < CAP) sts32(sbuf + 4u * (unsigned)(k * CAP + o), slot);
       }
       cnt[k] += __popc(m);
     }
@@ -132,13 +147,13 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
   const int grp = lane >> 3, sub = lane & 7;
   auto process_table = [&](int n_ent) {
     __syncwarp();
-    // U trips per loop iteration: all 3*U candidate loads are issued before the
+    // U trips per loop iteration: all candidate loads are issued before the
     // first test, so one memory latency is paid per U trips, not per trip.
-    constexpr int U = 4;
-    for (int e0 = grp; e0 < n_ent + grp; e0 += 4 * U) {   // uniform trip count: (e0 - grp) < n_ent
+    constexpr int U = FUSED_U;
+    for (int e0 = grp; e0 < n_ent + grp; e0 += 4 * U) {  // uniform trip count: (e0 - grp) < n_ent
       int jj[U];
       bool vv[U];
-      double px[U], py[U], pz[U], pw[U];
+      Cand<D> c[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int e = e0 + 4 * u;
@@ -147,16 +162,11 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
         jj[u] = vv[u] ? (ent >> 4) + sub : 0;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        px[u] = sx[jj[u]];
-        py[u] = sy[jj[u]];
-        pz[u] = D >= 3 ? sz[jj[u]] : 0.0;
-        pw[u] = D >= 4 ? sw[jj[u]] : 0.0;
-      }
+      for (int u = 0; u < U; ++u) c[u] = load_cand<D>(g, jj[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (e0 - grp + 4 * u < n_ent)   // warp-uniform: skip trips past the end of the table
-          visit(vv[u], jj[u], px[u], py[u], pz[u], pw[u]);
+        if (e0 - grp + 4 * u < n_ent)  // warp-uniform: skip trips past the end of the table
+          visit(vv[u], jj[u], c[u].x, c[u].y, c[u].z, c[u].w);
       }
     }
     __syncwarp();
@@ -165,7 +175,6 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
   bool any_live = false;
 #pragma unroll
   for (int k = 0; k < QN; ++k) any_live |= G.live[k];
-
   if (g.n_sorted > 0 && any_live) {
     // union of the group's row ranges
     int cy0 = 0x7fffffff, cy1 = -1, cz0 = 0x7fffffff, cz1 = -1;
@@ -188,7 +197,7 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
     const int nrows = wy * (cz1 - cz0 + 1);
     int tot = 0;  // entries currently in the table
     for (int rb = 0; rb < nrows; rb += 32) {
-      // lane <-> row: union over the group's queries of the reachable cells
+      // lane <-> row: reachable cells of the row for the group's query box
       int sa = 0, sb = 0;
       const int row = rb + lane;
       if (row < nrows) {
@@ -244,67 +253,58 @@ __device__ __forceinline__ void scan_group(const GridView &g, const FGrid &fg, c
     }
 }
 
-// Dense flush of one query's buffered hits: all lanes hold a hit.
+// Dense flush of one query's buffered hits: all lanes hold a hit.  Full groups of 4 x 32 hits run
+// without predicates, the remainder is predicated.
 template <int D, bool TAIL>
 __device__ __forceinline__ void flush_hits(const GridView &g, const double *q, unsigned sbuf_k, int n, int lane,
                                            int32_t *__restrict__ oi, double *__restrict__ od) {
-  const double *__restrict__ sx = g.sx;
-  const double *__restrict__ sy = g.sy;
-  const double *__restrict__ sz = g.sz;
-  const double *__restrict__ sw = g.sw;
-  const int *__restrict__ sperm = g.sperm;
   constexpr int U = 4;
-  for (int h0 = lane; h0 < n + lane; h0 += 32 * U) {   // (h0 - lane) < n: uniform trips
+  auto fetch = [&](int slot, int &node, double &px, double &py, double &pz, double &pw) {
+    if (!TAIL || slot >= 0) {
+      // SoA gathers: consecutive hits sit in consecutive slots, so these are nearly coalesced.  (A packed
+      // 32-byte (x,y,z,node) record per slot was tried for scan and flush: more L1 wavefronts, slower.)
+      px = g.sx[slot]; py = g.sy[slot]; pz = D >= 3 ? g.sz[slot] : 0.0; pw = D >= 4 ? g.sw[slot] : 0.0;
+      node = g.sperm[slot];
+    } else {
+      node = -(slot + 1);
+      const double4 pp = g.pos[node];
+      px = pp.x; py = pp.y; pz = pp.z; pw = pp.w;
+    }
+  };
+  const int n_full = (n / (32 * U)) * (32 * U);
+  for (int h0 = lane; h0 < n_full; h0 += 32 * U) {
     int node[U];
     double px[U], py[U], pz[U], pw[U];
-    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) fetch(lds32(sbuf_k + 4u * (unsigned)(h0 + 32 * u)), node[u], px[u], py[u], pz[u], pw[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int h = h0 + 32 * u;
-      ok[u] = h < n;
-      const int slot = ok[u] ? lds32(sbuf_k + 4u * (unsigned)h) : 0;
-      px[u] = 0.0;
-      py[u] = 0.0;
-      pz[u] = 0.0;
-      pw[u] = 0.0;
-      node[u] = 0;
-      if (!ok[u]) continue;   // nothing to load (the sorted arrays may not even exist)
-      if (!TAIL || slot >= 0) {
-        px[u] = sx[slot];
-        py[u] = sy[slot];
-        if (D >= 3) pz[u] = sz[slot];
-        if (D >= 4) pw[u] = sw[slot];
-        node[u] = sperm[slot];
-      } else {
-        node[u] = -(slot + 1);
-        const double4 pp = g.pos[node[u]];
-        px[u] = pp.x; py[u] = pp.y; pz[u] = pp.z; pw[u] = pp.w;
-      }
+      oi[h0 + 32 * u] = node[u];
+      if (od) od[h0 + 32 * u] = __dsqrt_rn(sqdist<D>(q, px[u], py[u], pz[u], pw[u]));
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int h = h0 + 32 * u;
-      if (ok[u]) {
-        oi[h] = node[u];
-        if (od) od[h] = __dsqrt_rn(sqdist<D>(q, px[u], py[u], pz[u], pw[u]));
-      }
-    }
+  }
+  for (int h = n_full + lane; h < n; h += 32) {
+    int node;
+    double px, py, pz, pw;
+    fetch(lds32(sbuf_k + 4u * (unsigned)h), node, px, py, pz, pw);
+    oi[h] = node;
+    if (od) od[h] = __dsqrt_rn(sqdist<D>(q, px, py, pz, pw));
   }
 }
 
-template <int D, int QN, int NW>
+template <int D, int QN, int NW, int CAP>
 __global__ void __launch_bounds__(NW * 32, 1)
 range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t *__restrict__ qorder, int64_t nq,
                    double r_uniform, double T_uniform, const double *__restrict__ ranges,
                    const double *__restrict__ Tq, int32_t *__restrict__ counts, int64_t *__restrict__ offsets,
                    int32_t *__restrict__ out_idx, double *__restrict__ out_dist, unsigned long long cap,
                    unsigned long long *__restrict__ cursor, int write_lists) {
-  extern __shared__ int s_buf[];  // [NW][QN][FUSED_CAP] hit slots, then [NW][FUSED_TAB] octet tables
+  extern __shared__ int s_buf[];  // [NW][QN][CAP] hit slots, then [NW][FUSED_TAB] octet tables
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
   const unsigned s0 = (unsigned)__cvta_generic_to_shared(s_buf);
-  const unsigned sbuf = pin_reg(s0 + 4u * (unsigned)(warp * QN * FUSED_CAP));
-  const unsigned stab = pin_reg(s0 + 4u * (unsigned)(NW * QN * FUSED_CAP + warp * FUSED_TAB));
+  const unsigned sbuf = pin_reg(s0 + 4u * (unsigned)(warp * QN * CAP));
+  const unsigned stab = pin_reg(s0 + 4u * (unsigned)(NW * QN * CAP + warp * FUSED_TAB));
   FGrid fg;
 #pragma unroll
   for (int c = 0; c < 3; ++c) { fg.inv[c] = (float)g.inv[c]; fg.cell[c] = (float)g.cell[c]; }
@@ -335,8 +335,7 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t
         G.rf[k] = __double2float_ru(ri) * (1.0f + 1e-6f);
         G.r2f[k] = __double2float_ru(ri * ri) * (1.0f + 1e-5f);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          G.ff[k][c] = c < D ? (float)((G.q[k][c] - g.lo[c]) * g.inv[c]) : 0.0f;
+        for (int c = 0; c < 3; ++c) G.ff[k][c] = c < D ? (float)((G.q[k][c] - g.lo[c]) * g.inv[c]) : 0.0f;
         // root (node 0) is admitted with <= (kdTree_general.jl:896-898): it needs
         // an explicit entry only when it sits exactly at distance r
         const double sr = sqdist<D>(G.q[k], p0.x, p0.y, p0.z, p0.w);
@@ -347,7 +346,7 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t
       int64_t base[QN];
 #pragma unroll
       for (int k = 0; k < QN; ++k) base[k] = 0;
-      scan_group<D, QN, false>(g, fg, G, lane, lt, sbuf, stab, cnt, base, nullptr, nullptr);
+      scan_group<D, QN, CAP, false>(g, fg, G, lane, lt, sbuf, stab, cnt, base, nullptr, nullptr);
 
       // reserve the exact output range of the group: one atomic per group
       unsigned long long need = 0;
@@ -361,7 +360,7 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t
       for (int k = 0; k < QN; ++k) {
         base[k] = (int64_t)b0;
         b0 += (unsigned long long)(cnt[k] + (root_extra[k] ? 1 : 0));
-        if (cnt[k] > FUSED_CAP) overflow = true;
+        if (cnt[k] > CAP) overflow = true;
         if (lane == 0 && G.qid[k] >= 0) {
           counts[G.qid[k]] = cnt[k] + (root_extra[k] ? 1 : 0);
           offsets[G.qid[k]] = base[k];
@@ -370,12 +369,12 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t
       if (!write_lists || b0 > cap) continue;  // counts only, or the lists do not fit (host retries)
       if (overflow) {
         int cnt2[QN];
-        scan_group<D, QN, true>(g, fg, G, lane, lt, sbuf, stab, cnt2, base, out_idx, out_dist);
+        scan_group<D, QN, CAP, true>(g, fg, G, lane, lt, sbuf, stab, cnt2, base, out_idx, out_dist);
       } else {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < QN; ++k) {
-          const unsigned sb_k = sbuf + 4u * (unsigned)(k * FUSED_CAP);
+          const unsigned sb_k = sbuf + 4u * (unsigned)(k * CAP);
           if (has_tail)
             flush_hits<D, true>(g, G.q[k], sb_k, cnt[k], lane, out_idx + base[k], out_dist ? out_dist + base[k] : nullptr);
           else
@@ -413,33 +412,25 @@ static double host_sqrt_thresh_lt(double r) {
   return t;
 }
 
-struct FusedTuning {
-  int qn = 2;
-  int nw = 24;
-};
-static FusedTuning fused_tuning() {
-  FusedTuning f;
-  if (const char *e = getenv("RRTQX_FUSED_QN")) f.qn = atoi(e);
-  if (const char *e = getenv("RRTQX_FUSED_NW")) f.nw = atoi(e);
-  return f;
-}
-
-template <int D, int QN, int NW>
+// Kernel variants: more warps per SM when the expected neighbour count is small, bigger hit buffers
+// (fewer warps) when it is large.  Shared memory per block = NW * (2*CAP + FUSED_TAB) * 4 bytes.
+template <int D, int NW, int CAP>
 static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, const int32_t *qorder, int64_t nq,
                          double r, double T, const double *dr, const double *dT, int32_t *counts, int64_t *offsets,
                          int32_t *idx, double *dist, unsigned long long cap, unsigned long long *cursor,
                          int write_lists) {
-  const size_t smem = (size_t)NW * (QN * FUSED_CAP + FUSED_TAB) * sizeof(int);
+  constexpr int QN = 2;
+  const size_t smem = (size_t)NW * (QN * CAP + FUSED_TAB) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    RQ_CUDA(cudaFuncSetAttribute(range_fused_kernel<D, QN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RQ_CUDA(cudaFuncSetAttribute(range_fused_kernel<D, QN, NW, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   constexpr int CHUNK = NW * QN * FUSED_ROUNDS;
   const int64_t n_chunks = (nq + CHUNK - 1) / CHUNK;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)ctx->sm_count));
-  range_fused_kernel<D, QN, NW><<<blocks, NW * 32, smem, ctx->stream>>>(g, dq, qorder, nq, r, T, dr, dT, counts, offsets,
-                                                                        idx, dist, cap, cursor, write_lists);
+  range_fused_kernel<D, QN, NW, CAP><<<blocks, NW * 32, smem, ctx->stream>>>(g, dq, qorder, nq, r, T, dr, dT, counts,
+                                                                             offsets, idx, dist, cap, cursor, write_lists);
   post_launch(ctx);
 }
 
@@ -474,22 +465,36 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
     cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
   }
-  const FusedTuning tune = fused_tuning();
+  // Expected neighbours per query (only selects the kernel variant): the uniform-density estimate
+  // n * V_ball(r) / V_grid with a 15 % margin; per-query radii take the large-buffer variant.
+  double k_est = 1e9;
+  if (!dr && r > 0.0 && std::isfinite(r)) {
+    double vol = 1.0;
+    int dims = 0;
+    const int nd[3] = {t->nx, t->ny, t->nz};
+    for (int c = 0; c < 3; ++c)
+      if (nd[c] > 1) { vol *= nd[c] * t->cell[c]; dims++; }
+    const double ball = dims == 3 ? 4.18879 * r * r * r : (dims == 2 ? 3.14159 * r * r : 2.0 * r);
+    k_est = dims ? 1.15 * (double)t->n * ball / vol : (double)t->n;
+  } else if (!dr) {
+    k_est = 0.0;
+  }
+  int variant = k_est <= 576.0 ? 0 : (k_est <= 1280.0 ? 1 : (k_est <= 2048.0 ? 2 : 3));
+  if (const char *e = getenv("RRTQX_FUSED_VARIANT")) variant = atoi(e);
   unsigned long long total = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     GridView g = t->view();
     RQ_CUDA(cudaMemsetAsync(res->cursor.p, 0, 4 * sizeof(unsigned long long), st));
     {
       PhaseScope p2(ctx, "range_fill");
-#define RQ_FUSED(QN_, NW_)                                                                                         \
-  launch_fused<D, QN_, NW_>(ctx, g, dq, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p,  \
-                            want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,               \
-                            count_only ? 0 : 1)
-      if (tune.qn == 1) {
-        if (tune.nw == 8) RQ_FUSED(1, 8); else if (tune.nw == 24) RQ_FUSED(1, 24); else RQ_FUSED(1, 16);
-      } else {
-        if (tune.nw == 8) RQ_FUSED(2, 8); else if (tune.nw == 24) RQ_FUSED(2, 24); else RQ_FUSED(2, 16);
-      }
+#define RQ_FUSED(NW_, CAP_)                                                                                          \
+  launch_fused<D, NW_, CAP_>(ctx, g, dq, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
+                             want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,             \
+                             count_only ? 0 : 1)
+      if (variant == 0) RQ_FUSED(28, 576);        // 28 warps/SM (72 registers), 158 KB shared; measured best of 20/24/28/32
+      else if (variant == 1) RQ_FUSED(20, 1280);  // 20 warps/SM, 225 KB
+      else if (variant == 2) RQ_FUSED(12, 2048);  // 12 warps/SM, 209 KB
+      else RQ_FUSED(6, 4096);                     //  6 warps/SM, 203 KB: up to 4096 neighbours buffered per query
 #undef RQ_FUSED
     }
     RQ_CUDA(cudaMemcpyAsync(&total, res->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, st));

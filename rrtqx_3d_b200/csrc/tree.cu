@@ -243,7 +243,8 @@ __global__ void cell_gather_kernel(const double4 *__restrict__ pos, const int32_
                                    double *__restrict__ sw) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  double4 p = pos[sperm[j]];
+  const int node = sperm[j];
+  double4 p = pos[node];
   sx[j] = p.x;
   sy[j] = p.y;
   sz[j] = p.z;
