@@ -19,6 +19,7 @@ struct rrtqx_range_result {
   rrtqx::DevBuf<int32_t> qkey, qorder, qhist, qstart;
   rrtqx::DevBuf<int32_t> scan_tmp32;
   rrtqx::DevBuf<int64_t> scan_tmp64;
+  rrtqx::DevBuf<double> qsorted;             // query coordinates in sorted order (valid when qbins > 0)
   int64_t qbins = 0;                        // bins of the last query sort (0: unsorted / iota order)
   rrtqx::DevBuf<double> tq;                  // per-query thresholds T_lt(r_q)
   rrtqx::DevBuf<unsigned long long> cursor;  // fused kernel: [0] output cursor, [1] chunk counter

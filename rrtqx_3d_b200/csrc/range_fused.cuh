@@ -294,7 +294,8 @@ __device__ __forceinline__ void flush_hits(const GridView &g, const double *q, u
 
 template <int D, int QN, int NW, int CAP>
 __global__ void __launch_bounds__(NW * 32, 1)
-range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t *__restrict__ qorder, int64_t nq,
+range_fused_kernel(GridView g, const double *__restrict__ queries, const double *__restrict__ qsorted,
+                   const int32_t *__restrict__ qorder, int64_t nq,
                    double r_uniform, double T_uniform, const double *__restrict__ ranges,
                    const double *__restrict__ Tq, int32_t *__restrict__ counts, int64_t *__restrict__ offsets,
                    int32_t *__restrict__ out_idx, double *__restrict__ out_dist, unsigned long long cap,
@@ -326,8 +327,10 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const int32_t
         const bool have = qfirst + k < nq;
         G.qid[k] = have ? qorder[qfirst + k] : -1;
         const int qq = have ? G.qid[k] : G.qid[0];
+        // coordinates: from the sorted copy when the batch was sorted (coalesced), else through qorder
+        const double *qsrc = qsorted ? qsorted + (have ? qfirst + k : qfirst) * D : queries + (int64_t)qq * D;
 #pragma unroll
-        for (int c = 0; c < D; ++c) G.q[k][c] = queries[(int64_t)qq * D + c];
+        for (int c = 0; c < D; ++c) G.q[k][c] = qsrc[c];
         const double r = have ? (ranges ? ranges[qq] : r_uniform) : -1.0;
         G.T[k] = have ? (Tq ? Tq[qq] : T_uniform) : -1.0;
         G.live[k] = have && (r > 0.0);
@@ -415,7 +418,7 @@ static double host_sqrt_thresh_lt(double r) {
 // Kernel variants: more warps per SM when the expected neighbour count is small, bigger hit buffers
 // (fewer warps) when it is large.  Shared memory per block = NW * (2*CAP + FUSED_TAB) * 4 bytes.
 template <int D, int NW, int CAP>
-static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, const int32_t *qorder, int64_t nq,
+static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, const double *dqs, const int32_t *qorder, int64_t nq,
                          double r, double T, const double *dr, const double *dT, int32_t *counts, int64_t *offsets,
                          int32_t *idx, double *dist, unsigned long long cap, unsigned long long *cursor,
                          int write_lists) {
@@ -429,7 +432,7 @@ static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, co
   constexpr int CHUNK = NW * QN * FUSED_ROUNDS;
   const int64_t n_chunks = (nq + CHUNK - 1) / CHUNK;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)ctx->sm_count));
-  range_fused_kernel<D, QN, NW, CAP><<<blocks, NW * 32, smem, ctx->stream>>>(g, dq, qorder, nq, r, T, dr, dT, counts,
+  range_fused_kernel<D, QN, NW, CAP><<<blocks, NW * 32, smem, ctx->stream>>>(g, dq, dqs, qorder, nq, r, T, dr, dT, counts,
                                                                              offsets, idx, dist, cap, cursor, write_lists);
   post_launch(ctx);
 }
@@ -488,7 +491,7 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     {
       PhaseScope p2(ctx, "range_fill");
 #define RQ_FUSED(NW_, CAP_)                                                                                          \
-  launch_fused<D, NW_, CAP_>(ctx, g, dq, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
+  launch_fused<D, NW_, CAP_>(ctx, g, dq, res->qbins > 0 ? res->qsorted.p : nullptr, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
                              want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,             \
                              count_only ? 0 : 1)
       if (variant == 0) RQ_FUSED(28, 576);        // 28 warps/SM (72 registers), 158 KB shared; measured best of 20/24/28/32
