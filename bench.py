@@ -447,6 +447,24 @@ def main():
             sms = float(np.mean(times))
             n_e = len(src)
             sbytes = args.nodes * 24 + n_e * 8 + args.sweep_obstacles * 40 + n_e * 1 + (n_eh + n_nh) * 4
+            # C5-style batch: explicitEdgeCheck(S, edge) of every edge against all 256 active spheres
+            dsrc, ddst = torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda()
+            dflag = torch.empty(len(src), dtype=torch.uint8, device="cuda")
+            from rrtqx_3d_b200.device import edge_check_batch
+            et = []
+            for it in range(3 + args.steps):
+                flush.zero_()
+                edge_check_batch(tree, S, dsrc, ddst, W.ROBOT_RADIUS, n_edges=len(src), out=dflag)
+                if it >= 3:
+                    et.append(ctx.last_phase_ms("edge_check"))
+            ems = float(np.mean(et))
+            line["edge_batch"] = {"workload": "explicitEdgeCheck(S, edge) for every C3 edge against all 256 spheres (device-resident)",
+                                  "edges": len(src), "obstacles": args.sweep_obstacles, "ms": ems,
+                                  "edges_per_s": len(src) / (ems / 1e3),
+                                  "edge_obstacle_pairs_per_s": len(src) * args.sweep_obstacles / (ems / 1e3),
+                                  "colliding_edges": int(dflag.sum().item()),
+                                  "algorithmic_bytes": len(src) * 9 + args.nodes * 32,
+                                  "hbm_frac": (len(src) * 9 + args.nodes * 32) / (ems / 1e3) / 1e9 / peak_gbs}
             line["edge_sweep"] = {"workload": "C3 obstacle-add sweep: 256 spheres vs all out-edges + parent edges of the 1M-node tree",
                                   "edges": n_e, "obstacles": args.sweep_obstacles, "pair_checks": n_tests,
                                   "candidate_nodes": n_cand, "blocked_edges": n_eh, "orphans": n_nh, "ms": sms,

@@ -1,5 +1,7 @@
 // collision.cu -- batched explicitEdgeCheck / explicitPointCheck against the
 // sphere obstacle list (DRRT_Q.jl:1434-1595, 1775-1826).
+#include <cstdlib>
+
 #include "objects.cuh"
 
 namespace rrtqx {
@@ -51,10 +53,12 @@ __global__ void sphere_table_kernel(const double4 *__restrict__ rec, const uint8
 }
 
 struct SphereTableBufs {
-  DevBuf<double4> rec;
-  DevBuf<double2> thr;
+  DevBuf<double4> rec, rec2;
+  DevBuf<double2> thr, thr2;
   DevBuf<int32_t> id;
   DevBuf<int32_t> n;
+  DevBuf<int32_t> cstart;
+  DevBuf<unsigned char> grid;  // SphGrid header
 };
 
 static SphereTableBufs &table_bufs(rrtqx_ctx *ctx) {
@@ -85,6 +89,152 @@ SphereTable build_sphere_table(rrtqx_ctx *ctx, const rrtqx_spheres *s, double ro
   t.n = (int)n;
   *n_dev_out = b.n.p;
   return t;
+}
+
+// ---------------------------------------------------------------- obstacle grid
+// For large edge batches the active-obstacle table is binned into a small uniform grid (cell >= 2 *
+// max(robotRadius + radius), at most 16^3 cells), so that an edge only meets the obstacles whose centre
+// lies within (half edge length + thr_max) of its midpoint.  Conservative: sphere o can only collide
+// if |c_o - mid| <= thr_o + L/2 (closePt lies on the segment), and the same monotone cell function bins
+// the centres and bounds the edge's box.  Obstacles with non-finite centre / threshold go to an
+// "always tested" bucket (the reference collides them with everything: !(NaN > x)).
+struct SphGrid {
+  int n_total;     // entries in the sorted table (binned + always)
+  int nx, ny, nz;  // cells; bucket nx*ny*nz is the "always" list
+  double lo[3], inv[3];
+  double thr_max;
+};
+constexpr int SG_MAX_DIM = 16;
+constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
+
+__device__ __forceinline__ int sg_cell(double v, double lo, double inv, int n) {
+  double c = floor((v - lo) * inv);
+  c = fmin(fmax(c, 0.0), (double)(n - 1));  // NaN -> 0
+  return (int)c;
+}
+
+__global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const double2 *__restrict__ thr,
+                                   const int32_t *__restrict__ n_live, double4 *__restrict__ rec2,
+                                   double2 *__restrict__ thr2, int32_t *__restrict__ cstart, SphGrid *__restrict__ G) {
+  __shared__ int hist[SG_MAX_CELLS + 2];
+  __shared__ double red[7][32];
+  __shared__ SphGrid g;
+  const int n = *n_live;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // bounding box of the finite centres and the largest finite threshold
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, tm = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double4 r = rec[i];
+    const double t = thr[i].x;
+    if (isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(t)) {
+      mn[0] = fmin(mn[0], r.x); mx[0] = fmax(mx[0], r.x);
+      mn[1] = fmin(mn[1], r.y); mx[1] = fmax(mx[1], r.y);
+      mn[2] = fmin(mn[2], r.z); mx[2] = fmax(mx[2], r.z);
+      tm = fmax(tm, t);
+    }
+  }
+  double v[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], tm};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(FULL, v[k], o);
+      v[k] = k < 3 ? fmin(v[k], w) : fmax(v[k], w);
+    }
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  for (int i = tid; i < SG_MAX_CELLS + 2; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    double r7[7];
+    for (int k = 0; k < 7; ++k) {
+      r7[k] = red[k][0];
+      for (int w = 1; w < nw; ++w) r7[k] = k < 3 ? fmin(r7[k], red[k][w]) : fmax(r7[k], red[k][w]);
+    }
+    g.thr_max = r7[6];
+    g.n_total = n;
+    int dims[3];
+    for (int c = 0; c < 3; ++c) {
+      const double ext = r7[3 + c] - r7[c];
+      double cell = fmax(2.0 * g.thr_max * (1.0 + 1e-9), ext / SG_MAX_DIM);
+      if (!(ext > 0.0) || !isfinite(ext) || !(cell > 0.0) || !isfinite(cell)) {
+        dims[c] = 1; g.lo[c] = 0.0; g.inv[c] = 0.0;
+      } else {
+        dims[c] = min(SG_MAX_DIM, (int)floor(ext / cell) + 1);
+        g.lo[c] = r7[c];
+        g.inv[c] = 1.0 / cell;
+      }
+    }
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    *G = g;
+  }
+  __syncthreads();
+  const int ncell = g.nx * g.ny * g.nz;
+  auto bucket = [&](int i) {
+    const double4 r = rec[i];
+    const double t = thr[i].x;
+    if (!(isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(t))) return ncell;  // always tested
+    return (sg_cell(r.z, g.lo[2], g.inv[2], g.nz) * g.ny + sg_cell(r.y, g.lo[1], g.inv[1], g.ny)) * g.nx +
+           sg_cell(r.x, g.lo[0], g.inv[0], g.nx);
+  };
+  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[bucket(i)], 1);
+  __syncthreads();
+  if (tid == 0) {  // exclusive scan (<= 4097 buckets)
+    int acc = 0;
+    for (int c = 0; c <= ncell; ++c) { const int h = hist[c]; hist[c] = acc; cstart[c] = acc; acc += h; }
+    cstart[ncell + 1] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int o = atomicAdd(&hist[bucket(i)], 1);
+    rec2[o] = rec[i];
+    thr2[o] = thr[i];
+  }
+}
+
+// One thread per edge against the binned obstacle table.
+template <bool FMA_DOT, bool SRC_TREE>
+__global__ void __launch_bounds__(256)
+edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                       const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
+                       const double4 *__restrict__ rec, const double2 *__restrict__ thr,
+                       const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ out) {
+  __shared__ SphGrid G;
+  if (threadIdx.x == 0) G = *Gp;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  SegPre pre;
+  if (SRC_TREE) {
+    const double4 a = pos[src[e]], b = pos[dst[e]];
+    pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+  } else {
+    const double *a = starts + 3 * e, *b = ends + 3 * e;
+    pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
+  }
+  const int ncell = G.nx * G.ny * G.nz;
+  bool hit = false;
+  auto run = [&](int a, int b) {
+    for (int o = a; o < b && !hit; ++o) {
+      const double4 r = rec[o];
+      const double2 t = thr[o];
+      hit = seg_sphere_collide<FMA_DOT>(pre, r.x, r.y, r.z, t.x, t.y);
+    }
+  };
+  if (!pre.cullable) {
+    run(0, G.n_total);  // degenerate edge: the reference collides it with every active obstacle
+  } else {
+    const double R = (pre.half + G.thr_max) * (1.0 + 1e-9) + 1e-300;
+    const int x0 = sg_cell(pre.mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(pre.mx + R, G.lo[0], G.inv[0], G.nx);
+    const int y0 = sg_cell(pre.my - R, G.lo[1], G.inv[1], G.ny), y1 = sg_cell(pre.my + R, G.lo[1], G.inv[1], G.ny);
+    const int z0 = sg_cell(pre.mz - R, G.lo[2], G.inv[2], G.nz), z1 = sg_cell(pre.mz + R, G.lo[2], G.inv[2], G.nz);
+    for (int z = z0; z <= z1 && !hit; ++z)
+      for (int y = y0; y <= y1 && !hit; ++y) {
+        const int base = (z * G.ny + y) * G.nx;
+        run(cstart[base + x0], cstart[base + x1 + 1]);
+      }
+    if (!hit) run(cstart[ncell], cstart[ncell + 1]);  // non-finite obstacles
+  }
+  out[e] = hit ? 1 : 0;
 }
 
 constexpr int SPH_TILE = 512;
@@ -158,14 +308,32 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
     const unsigned blocks = (unsigned)div_up(n_edges, TB);
     const double4 *pos = from_tree ? tree->pos.p : nullptr;
     const bool fma = flags & RRTQX_CHECK_FMA_DOT;
-    if (from_tree) {
+    if (n_edges >= 4096 && spheres->n >= 16 && !getenv("RRTQX_EDGE_NO_GRID")) {
+      // large batch: bin the obstacles once, then each edge meets only the obstacles around it
+      SphereTableBufs &b = table_bufs(ctx);
+      b.rec2.ensure((size_t)spheres->n + 1, st);
+      b.thr2.ensure((size_t)spheres->n + 1, st);
+      b.cstart.ensure(SG_MAX_CELLS + 4, st);
+      b.grid.ensure(sizeof(SphGrid) + 16, st);
+      SphGrid *dG = (SphGrid *)b.grid.p;
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, n_live, b.rec2.p, b.thr2.p, b.cstart.p, dG);
+      if (from_tree) {
+        if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+        else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+      } else {
+        if (fma) edge_check_grid_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+        else     edge_check_grid_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+      }
+      post_launch(ctx, 2);
+    } else if (from_tree) {
       if (fma) edge_check_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
       else     edge_check_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
+      post_launch(ctx);
     } else {
       if (fma) edge_check_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
       else     edge_check_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
+      post_launch(ctx);
     }
-    post_launch(ctx);
   }
   if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n_edges);
   RQ_CUDA(cudaStreamSynchronize(st));

@@ -235,3 +235,33 @@ def test_polygon_world_segment_and_dubins_checks(ctx):
     # inactive obstacles are skipped
     P.upload(obstacles, active=np.zeros(len(obstacles)))
     assert not segment_check_2d_batch(P, starts, ends, rad).any()
+
+
+def test_edge_check_grid_path_pathological_obstacles(ctx, building2):
+    """Large batches bin the obstacles into a grid; obstacles the reference collides with everything
+    (NaN centre -> !(NaN > thr)) or with huge radii must still be met by every edge."""
+    centers, radii, _ = building2
+    pts, _, _ = W.c2_workload(30000, 1)
+    n_e = 50000
+    u = W.splitmix64(78, 0, 2 * n_e)
+    src = (u[:n_e] % np.uint64(len(pts))).astype(np.int32)
+    dst = ((u[:n_e] + u[n_e:] % np.uint64(50)) % np.uint64(len(pts))).astype(np.int32)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts)
+    for variant in ("nan_centre", "inf_radius", "far_outlier", "single_cell"):
+        c, r = centers.copy(), radii.copy()
+        if variant == "nan_centre":
+            c[5, 1] = np.nan
+        elif variant == "inf_radius":
+            r[7] = np.inf
+        elif variant == "far_outlier":
+            c[3] = [1e6, -1e6, 1e6]
+        else:
+            c[:] = c[0]                       # all obstacles at one point: degenerate grid extents
+        S = SphereSet(ctx, c, r)
+        sph, ns = oracle.make_spheres(c, r)
+        got = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS)
+        want = _orc_edges(sph, ns, pts, src, dst, W.ROBOT_RADIUS)
+        assert np.array_equal(got, want), variant
+        if variant in ("nan_centre", "inf_radius"):
+            assert got.all()
