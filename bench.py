@@ -437,13 +437,20 @@ def main():
             S = SphereSet(ctx, centers, radii)
             ids = np.arange(args.sweep_obstacles, dtype=np.int32)
             sres = SweepResult(ctx)
-            times = []
+            from rrtqx_3d_b200 import _abi as A
+            times, times_stats = [], []
             for it in range(3 + args.steps):
                 flush.zero_()
-                E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA, result=sres)
+                E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS, result=sres)   # node-centric + statistics
+                if it >= 3:
+                    times_stats.append(ctx.last_phase_ms("add_sweep"))
+            n_eh, n_nh, n_cand, n_tests = sres.sizes()
+            for it in range(3 + args.steps):
+                flush.zero_()
+                E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA, result=sres)                        # edge-centric (default)
                 if it >= 3:
                     times.append(ctx.last_phase_ms("add_sweep"))
-            n_eh, n_nh, n_cand, n_tests = sres.sizes()
+            assert sres.sizes()[:2] == (n_eh, n_nh)
             sms = float(np.mean(times))
             n_e = len(src)
             sbytes = args.nodes * 24 + n_e * 8 + args.sweep_obstacles * 40 + n_e * 1 + (n_eh + n_nh) * 4
@@ -468,6 +475,7 @@ def main():
             line["edge_sweep"] = {"workload": "C3 obstacle-add sweep: 256 spheres vs all out-edges + parent edges of the 1M-node tree",
                                   "edges": n_e, "obstacles": args.sweep_obstacles, "pair_checks": n_tests,
                                   "candidate_nodes": n_cand, "blocked_edges": n_eh, "orphans": n_nh, "ms": sms,
+                                  "ms_with_statistics_kernel": float(np.mean(times_stats)),
                                   "edges_per_s": n_e / (sms / 1e3), "pair_checks_per_s": n_tests / (sms / 1e3),
                                   "algorithmic_bytes": sbytes, "hbm_frac": sbytes / (sms / 1e3) / 1e9 / peak_gbs}
         except Exception as exc:  # the headline line must still be printed

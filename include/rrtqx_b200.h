@@ -297,7 +297,11 @@ RRTQX_API rrtqx_status rrtqx_obstacle_add_sweep(rrtqx_edges *edges,
  * predicate :3330 to build that list).  QX behaviour (obstacle disabled before
  * the loop, nothing restored) is the caller passing
  * RRTQX_SWEEP_REMOVED_INACTIVE. */
-enum { RRTQX_SWEEP_REMOVED_INACTIVE = 16u };
+enum {
+  RRTQX_SWEEP_REMOVED_INACTIVE = 16u,
+  RRTQX_SWEEP_STATS = 32u /* add sweep: also count candidate nodes and (edge, obstacle) pairs (node-centric
+                             kernel, slower); without it n_candidates / n_pair_tests are reported as -1 */
+};
 RRTQX_API rrtqx_status rrtqx_obstacle_remove_sweep(
     rrtqx_edges *edges, const rrtqx_spheres *spheres, int32_t ob_id,
     const int32_t *other_ids, int64_t n_others, const uint8_t *edge_dist_inf,

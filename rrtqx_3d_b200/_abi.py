@@ -20,6 +20,7 @@ ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_EMPTY_TREE, ERR_UNSUPPORTED, ERR_STATE = 1
 RANGE_WANT_DIST, RANGE_COUNT_ONLY = 1, 2
 CHECK_FMA_DOT, CHECK_IGNORE_ACTIVE, CHECK_QUICK_PASS = 1, 2, 4
 SWEEP_REMOVED_INACTIVE = 16
+SWEEP_STATS = 32
 
 vp = C.c_void_p
 i32, i64, u32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_double

@@ -91,106 +91,6 @@ SphereTable build_sphere_table(rrtqx_ctx *ctx, const rrtqx_spheres *s, double ro
   return t;
 }
 
-// ---------------------------------------------------------------- obstacle grid
-// For large edge batches the active-obstacle table is binned into a small uniform grid (cell >= 2 *
-// max(robotRadius + radius), at most 16^3 cells), so that an edge only meets the obstacles whose centre
-// lies within (half edge length + thr_max) of its midpoint.  Conservative: sphere o can only collide
-// if |c_o - mid| <= thr_o + L/2 (closePt lies on the segment), and the same monotone cell function bins
-// the centres and bounds the edge's box.  Obstacles with non-finite centre / threshold go to an
-// "always tested" bucket (the reference collides them with everything: !(NaN > x)).
-struct SphGrid {
-  int n_total;     // entries in the sorted table (binned + always)
-  int nx, ny, nz;  // cells; bucket nx*ny*nz is the "always" list
-  double lo[3], inv[3];
-  double thr_max;
-};
-constexpr int SG_MAX_DIM = 16;
-constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
-
-__device__ __forceinline__ int sg_cell(double v, double lo, double inv, int n) {
-  double c = floor((v - lo) * inv);
-  c = fmin(fmax(c, 0.0), (double)(n - 1));  // NaN -> 0
-  return (int)c;
-}
-
-__global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const double2 *__restrict__ thr,
-                                   const int32_t *__restrict__ n_live, double4 *__restrict__ rec2,
-                                   double2 *__restrict__ thr2, int32_t *__restrict__ cstart, SphGrid *__restrict__ G) {
-  __shared__ int hist[SG_MAX_CELLS + 2];
-  __shared__ double red[7][32];
-  __shared__ SphGrid g;
-  const int n = *n_live;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  // bounding box of the finite centres and the largest finite threshold
-  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, tm = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const double4 r = rec[i];
-    const double t = thr[i].x;
-    if (isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(t)) {
-      mn[0] = fmin(mn[0], r.x); mx[0] = fmax(mx[0], r.x);
-      mn[1] = fmin(mn[1], r.y); mx[1] = fmax(mx[1], r.y);
-      mn[2] = fmin(mn[2], r.z); mx[2] = fmax(mx[2], r.z);
-      tm = fmax(tm, t);
-    }
-  }
-  double v[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], tm};
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    for (int o = 16; o > 0; o >>= 1) {
-      const double w = __shfl_xor_sync(FULL, v[k], o);
-      v[k] = k < 3 ? fmin(v[k], w) : fmax(v[k], w);
-    }
-    if (lane == 0) red[k][warp] = v[k];
-  }
-  for (int i = tid; i < SG_MAX_CELLS + 2; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  if (tid == 0) {
-    double r7[7];
-    for (int k = 0; k < 7; ++k) {
-      r7[k] = red[k][0];
-      for (int w = 1; w < nw; ++w) r7[k] = k < 3 ? fmin(r7[k], red[k][w]) : fmax(r7[k], red[k][w]);
-    }
-    g.thr_max = r7[6];
-    g.n_total = n;
-    int dims[3];
-    for (int c = 0; c < 3; ++c) {
-      const double ext = r7[3 + c] - r7[c];
-      double cell = fmax(2.0 * g.thr_max * (1.0 + 1e-9), ext / SG_MAX_DIM);
-      if (!(ext > 0.0) || !isfinite(ext) || !(cell > 0.0) || !isfinite(cell)) {
-        dims[c] = 1; g.lo[c] = 0.0; g.inv[c] = 0.0;
-      } else {
-        dims[c] = min(SG_MAX_DIM, (int)floor(ext / cell) + 1);
-        g.lo[c] = r7[c];
-        g.inv[c] = 1.0 / cell;
-      }
-    }
-    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
-    *G = g;
-  }
-  __syncthreads();
-  const int ncell = g.nx * g.ny * g.nz;
-  auto bucket = [&](int i) {
-    const double4 r = rec[i];
-    const double t = thr[i].x;
-    if (!(isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(t))) return ncell;  // always tested
-    return (sg_cell(r.z, g.lo[2], g.inv[2], g.nz) * g.ny + sg_cell(r.y, g.lo[1], g.inv[1], g.ny)) * g.nx +
-           sg_cell(r.x, g.lo[0], g.inv[0], g.nx);
-  };
-  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[bucket(i)], 1);
-  __syncthreads();
-  if (tid == 0) {  // exclusive scan (<= 4097 buckets)
-    int acc = 0;
-    for (int c = 0; c <= ncell; ++c) { const int h = hist[c]; hist[c] = acc; cstart[c] = acc; acc += h; }
-    cstart[ncell + 1] = acc;
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int o = atomicAdd(&hist[bucket(i)], 1);
-    rec2[o] = rec[i];
-    thr2[o] = thr[i];
-  }
-}
-
 // One thread per edge against the binned obstacle table.
 template <bool FMA_DOT, bool SRC_TREE>
 __global__ void __launch_bounds__(256)
@@ -316,7 +216,7 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
       b.cstart.ensure(SG_MAX_CELLS + 4, st);
       b.grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)b.grid.p;
-      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, n_live, b.rec2.p, b.thr2.p, b.cstart.p, dG);
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG);
       if (from_tree) {
         if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
         else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);

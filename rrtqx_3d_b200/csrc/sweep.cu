@@ -107,14 +107,17 @@ void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
 // ------------------------------------------------------ sweep obstacle table
 __global__ void sweep_table_kernel(const double4 *__restrict__ rec, const int32_t *__restrict__ ids, int n,
                                    double robot_radius, double delta, double4 *__restrict__ out_rec,
-                                   double4 *__restrict__ out_par) {
+                                   double4 *__restrict__ out_par, double2 *__restrict__ out_thr,
+                                   double2 *__restrict__ out_ext) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 r = rec[ids[i]];
   double thr = __dadd_rn(robot_radius, r.w);                       // DRRT_Q.jl:1790
   double sr = __dadd_rn(__dadd_rn(robot_radius, delta), r.w);     // :3203 searchRange, left to right
   out_rec[i] = r;
-  out_par[i] = make_double4(thr, sqrt_thresh_le(thr), sqrt_thresh_lt(sr), sr);
+  const double4 par = make_double4(thr, sqrt_thresh_le(thr), sqrt_thresh_lt(sr), sr);
+  out_par[i] = par;
+  if (out_thr) { out_thr[i] = make_double2(par.x, par.y); out_ext[i] = make_double2(par.z, par.w); }
 }
 
 constexpr int SW_TILE = 256;  // obstacles per shared-memory tile
@@ -216,6 +219,68 @@ add_sweep_kernel(const double4 *__restrict__ pos, int n_nodes, const int32_t *__
   }
   __syncthreads();
   if (threadIdx.x < 2) atomicAdd(&stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// addNewObstacle, edge-centric form (no statistics): one thread per out-edge and per parent edge, the
+// sweep's obstacles binned into the obstacle grid.  Blocked <=> some obstacle o collides with the edge
+// AND the edge's START node passes o's start-node filter dist(c_o, v) < searchRange_o (root: <=), the
+// reference's candidate rule (findPointsInConflictWithObstacle).  The filter is evaluated only for the
+// few obstacles that actually collide; for edges shorter than delta it is implied by the collision.
+template <bool FMA_DOT>
+__global__ void __launch_bounds__(256)
+add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src,
+                      const int32_t *__restrict__ dst, int64_t n_edges, const int32_t *__restrict__ parent,
+                      const double4 *__restrict__ rec, const double2 *__restrict__ thr, const double2 *__restrict__ ext,
+                      const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ edge_flag,
+                      uint8_t *__restrict__ node_flag) {
+  __shared__ SphGrid G;
+  if (threadIdx.x == 0) G = *Gp;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_edges + n_nodes) return;
+  const bool is_parent = i >= n_edges;
+  int v, w;
+  if (is_parent) {
+    v = (int)(i - n_edges);
+    w = parent ? parent[v] : -1;
+    if (w < 0) return;
+  } else {
+    v = src[i];
+    w = dst[i];
+  }
+  const double4 a = pos[v], b = pos[w];
+  const SegPre pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+  bool hit = false;
+  auto run = [&](int lo, int hi) {
+    for (int o = lo; o < hi && !hit; ++o) {
+      const double4 r = rec[o];
+      const double2 t = thr[o];
+      if (seg_sphere_collide<FMA_DOT>(pre, r.x, r.y, r.z, t.x, t.y)) {
+        const double q[3] = {r.x, r.y, r.z};
+        const double s = sqdist<3>(q, a.x, a.y, a.z, 0.0);  // euclid(ob.position, startNode.position)
+        const double2 e = ext[o];
+        hit = (s < e.x) || (v == 0 && __dsqrt_rn(s) <= e.y);
+      }
+    }
+  };
+  const int ncell = G.nx * G.ny * G.nz;
+  if (!pre.cullable) {
+    run(0, G.n_total);
+  } else {
+    const double R = (pre.half + G.thr_max) * (1.0 + 1e-9) + 1e-300;
+    const int x0 = sg_cell(pre.mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(pre.mx + R, G.lo[0], G.inv[0], G.nx);
+    const int y0 = sg_cell(pre.my - R, G.lo[1], G.inv[1], G.ny), y1 = sg_cell(pre.my + R, G.lo[1], G.inv[1], G.ny);
+    const int z0 = sg_cell(pre.mz - R, G.lo[2], G.inv[2], G.nz), z1 = sg_cell(pre.mz + R, G.lo[2], G.inv[2], G.nz);
+    for (int z = z0; z <= z1 && !hit; ++z)
+      for (int y = y0; y <= y1 && !hit; ++y) {
+        const int base = (z * G.ny + y) * G.nx;
+        run(cstart[base + x0], cstart[base + x1 + 1]);
+      }
+    if (!hit) run(cstart[ncell], cstart[ncell + 1]);
+  }
+  if (hit) {
+    if (is_parent) node_flag[v] = 1; else edge_flag[i] = 1;
+  }
 }
 
 // removeObstacle: one thread per edge (upload order).  ob = table entry 0,
@@ -331,11 +396,37 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
   const int32_t *dids = to_device(ctx, ob_ids, (size_t)n_obs, R->ids_stage);
   PhaseScope ph(ctx, "add_sweep");
   prepare_result(E, R);
+  bool no_stats = false;
   if (n_obs > 0 && E->n_nodes > 0) {
     R->ob_rec.ensure((size_t)n_obs, st);
     R->ob_par.ensure((size_t)n_obs, st);
+    R->ob_thr.ensure((size_t)n_obs, st);
+    R->ob_ext.ensure((size_t)n_obs, st);
     const int TB = 256;
-    sweep_table_kernel<<<div_up(n_obs, TB), TB, 0, st>>>(S->rec.p, dids, (int)n_obs, robot_radius, delta, R->ob_rec.p, R->ob_par.p);
+    sweep_table_kernel<<<div_up(n_obs, TB), TB, 0, st>>>(S->rec.p, dids, (int)n_obs, robot_radius, delta, R->ob_rec.p, R->ob_par.p, R->ob_thr.p, R->ob_ext.p);
+    if (!(flags & RRTQX_SWEEP_STATS)) {
+      // edge-centric sweep over the obstacle grid (no candidate / pair statistics)
+      R->ob_rec2.ensure((size_t)n_obs + 1, st);
+      R->ob_thr2.ensure((size_t)n_obs + 1, st);
+      R->ob_ext2.ensure((size_t)n_obs + 1, st);
+      R->cstart.ensure(SG_MAX_CELLS + 4, st);
+      R->grid.ensure(sizeof(SphGrid) + 16, st);
+      SphGrid *dG = (SphGrid *)R->grid.p;
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
+                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG);
+      const int64_t work = E->n_edges + E->n_nodes;
+      const int32_t *par = E->has_parent ? E->parent.p : nullptr;
+      if (flags & RRTQX_CHECK_FMA_DOT)
+        add_sweep_edge_kernel<true><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
+                                                                     R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG,
+                                                                     R->edge_flag.p, R->node_flag.p);
+      else
+        add_sweep_edge_kernel<false><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
+                                                                      R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG,
+                                                                      R->edge_flag.p, R->node_flag.p);
+      post_launch(ctx, 3);
+      no_stats = true;
+    } else {
     const int blocks = std::max(1, std::min(div_up(E->n_nodes * 32, TB), ctx->sm_count * 8));
     const int32_t *par = E->has_parent ? E->parent.p : nullptr;
     if (flags & RRTQX_CHECK_FMA_DOT)
@@ -347,8 +438,10 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
                                                      E->lmax.p, E->degenerate.p, R->ob_rec.p, R->ob_par.p, (int)n_obs,
                                                      R->edge_flag.p, R->node_flag.p, R->stats.p);
     post_launch(ctx, 2);
+    }
   }
   finish_sweep(ctx, R);
+  if (no_stats) { R->n_candidates = -1; R->n_pair_tests = -1; }
 }
 
 void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id, const int32_t *other_ids,
@@ -379,7 +472,7 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
   R->ob_rec.ensure((size_t)n_tab, st);
   R->ob_par.ensure((size_t)n_tab, st);
   const int TB = 256;
-  sweep_table_kernel<<<div_up(n_tab, TB), TB, 0, st>>>(S->rec.p, R->ids_stage2.p, n_tab, robot_radius, delta, R->ob_rec.p, R->ob_par.p);
+  sweep_table_kernel<<<div_up(n_tab, TB), TB, 0, st>>>(S->rec.p, R->ids_stage2.p, n_tab, robot_radius, delta, R->ob_rec.p, R->ob_par.p, nullptr, nullptr);
   post_launch(ctx);
   if (E->n_edges > 0) {
     const int removed_inactive = (flags & RRTQX_SWEEP_REMOVED_INACTIVE) ? 1 : 0;

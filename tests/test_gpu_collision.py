@@ -117,9 +117,12 @@ def test_obstacle_add_and_remove_sweep(ctx):
     E = EdgeSet(t)
     E.upload(src, dst, parent)
     ob_ids = np.arange(len(radii), dtype=np.int32)
-    res = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA)
+    res = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS)   # node-centric kernel + statistics
     ge, gn = res.fetch()
     n_eh, n_nh, n_cand, n_tests = res.sizes()
+    fast = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA)                         # edge-centric kernel (default)
+    fe, fn = fast.fetch()
+    assert np.array_equal(fe, ge) and np.array_equal(fn, gn) and fast.sizes()[2:] == (-1, -1)
 
     # oracle: CSR in edge-id order per start node
     orc = oracle.KDTree(3)

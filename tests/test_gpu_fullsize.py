@@ -94,14 +94,18 @@ def test_c3_full_size_sweep_is_union_of_single_obstacle_sweeps(ctx, c2):
     S = SphereSet(ctx, centers, radii)
     E = EdgeSet(t)
     E.upload(src, dst, parent)
-    full = E.add_sweep(S, np.arange(256, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA)
+    from rrtqx_3d_b200 import _abi as A
+    fast = E.add_sweep(S, np.arange(256, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA)          # edge-centric (default)
+    full = E.add_sweep(S, np.arange(256, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS)
     fe, fn = full.fetch()
+    qe, qn = fast.fetch()
+    assert np.array_equal(qe, fe) and np.array_equal(qn, fn)                                # both kernels agree
     n_eh, n_nh, n_cand, n_tests = full.sizes()
     assert len(fe) == n_eh > 1e6 and len(fn) == n_nh
     # linearity: OR over obstacles == union of disjoint obstacle groups; statistics add up
     ue, un, cand, tests = set(), set(), 0, 0
     for lo in range(0, 256, 64):
-        part = E.add_sweep(S, np.arange(lo, lo + 64, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA)
+        part = E.add_sweep(S, np.arange(lo, lo + 64, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS)
         pe, pn = part.fetch()
         ue.update(pe.tolist()); un.update(pn.tolist())
         cand += part.sizes()[2]; tests += part.sizes()[3]
