@@ -956,3 +956,191 @@ int orc_edge_check_dubins(const orc_obstacle2d *ob, const double *start_pos,
       return 1;
   return 0;
 }
+
+/* ------------------------------------------------ Dubins trajectory (solver) */
+
+/* DRRT_distance_functions.jl:62-80 */
+static double right_turn_dist(const double *a, const double *b, const double *c, double r) {
+  double theta = atan2(a[1] - c[1], a[0] - c[0]) - atan2(b[1] - c[1], b[0] - c[0]);
+  if (theta < 0) theta = theta + 2 * 3.141592653589793;
+  return theta * r;
+}
+static double left_turn_dist(const double *a, const double *b, const double *c, double r) {
+  double theta = atan2(b[1] - c[1], b[0] - c[0]) - atan2(a[1] - c[1], a[0] - c[0]);
+  if (theta < 0) theta = theta + 2 * 3.141592653589793;
+  return theta * r;
+}
+static double dist2d(const double *a, const double *b) {
+  double dx = a[0] - b[0], dy = a[1] - b[1];
+  return sqrt(dx * dx + dy * dy);
+}
+
+/* appends the arc  centre + r*[cos(phi), sin(phi)]  for phi = collect(phi_start:step:phi_end)
+ * (or the single angle phi_start when they are equal), DRRT_DubinsEdge_functions.jl:520-528 etc.
+ * Julia's float range is TwicePrecision; here length = floor((stop-start)/step)+1 and element i =
+ * start + i*step in plain binary64 -- agrees to ~1 ulp (parity by tolerance). */
+static int emit_arc(const double *c, double r, double phi_start, double phi_end, double step, double *out, int n,
+                    int cap) {
+  int cnt = 1;
+  if (phi_end != phi_start) {
+    double q = (phi_end - phi_start) / step;
+    cnt = (q >= 0.0) ? (int)floor(q) + 1 : 0;
+  }
+  for (int i = 0; i < cnt; ++i) {
+    double phi = phi_start + (double)i * step;
+    if (n < cap) { out[2 * n] = c[0] + r * cos(phi); out[2 * n + 1] = c[1] + r * sin(phi); }
+    n += 1;
+  }
+  return n;
+}
+
+/* calculateTrajectory(S, edge::DubinsEdge), space without time: DRRT_DubinsEdge_functions.jl:329-709.
+ * start4 / goal4 = [x y t theta].  type: 0 rsl, 1 rsr, 2 rlr, 3 lsr, 4 lsl, 5 lrl, -1 none.
+ * Returns the number of trajectory points (written up to cap). */
+int orc_dubins_trajectory(const double *start4, const double *goal4, double r_min, double *dist_out,
+                          int32_t *type_out, double *traj_xy, int32_t cap) {
+  const double PI = 3.141592653589793;
+  const double il[2] = {start4[0], start4[1]}, gl[2] = {goal4[0], goal4[1]};
+  const double ith = start4[3], gth = goal4[3];
+  const double irc[2] = {il[0] + r_min * cos(ith - PI / 2.0), il[1] + r_min * sin(ith - PI / 2.0)};
+  const double ilc[2] = {il[0] + r_min * cos(ith + PI / 2.0), il[1] + r_min * sin(ith + PI / 2.0)};
+  const double grc[2] = {gl[0] + r_min * cos(gth - PI / 2.0), gl[1] + r_min * sin(gth - PI / 2.0)};
+  const double glc[2] = {gl[0] + r_min * cos(gth + PI / 2.0), gl[1] + r_min * sin(gth + PI / 2.0)};
+  double best = INFINITY;
+  int type = -1;
+  double D, v[2], R;
+  /* r-s-l :373-397 */
+  double rsl1[2] = {0, 0}, rsl2[2] = {0, 0};
+  D = dist2d(glc, irc);
+  v[0] = (glc[0] - irc[0]) / D; v[1] = (glc[1] - irc[1]) / D;
+  R = -2.0 * r_min / D;
+  if (!(fabs(R) > 1.0)) {
+    double sq = sqrt(1.0 - R * R);
+    double a = r_min * (R * v[0] + v[1] * sq), b = r_min * (R * v[1] - v[0] * sq);
+    rsl1[0] = irc[0] - a; rsl2[0] = glc[0] + a;
+    rsl1[1] = irc[1] - b; rsl2[1] = glc[1] + b;
+    double len = right_turn_dist(il, rsl1, irc, r_min) + dist2d(rsl2, rsl1) + left_turn_dist(rsl2, gl, glc, r_min);
+    if (best > len) { best = len; type = 0; }
+  }
+  /* r-s-r :400-415 */
+  double rsr1[2], rsr2[2];
+  D = dist2d(grc, irc);
+  v[0] = (grc[0] - irc[0]) / D; v[1] = (grc[1] - irc[1]) / D;
+  rsr1[0] = -r_min * v[1] + irc[0]; rsr2[0] = -r_min * v[1] + grc[0];
+  rsr1[1] = r_min * v[0] + irc[1];  rsr2[1] = r_min * v[0] + grc[1];
+  {
+    double len = right_turn_dist(il, rsr1, irc, r_min) + dist2d(rsr2, rsr1) + right_turn_dist(rsr2, gl, grc, r_min);
+    if (best > len) { best = len; type = 1; }
+  }
+  /* r-l-r :418-433 (uses D, v of the r-s-r block) */
+  double rlr_rl[2] = {NAN, NAN}, rlr_lr[2] = {NAN, NAN}, rlr_c[2] = {NAN, NAN};
+  if (D < 4.0 * r_min) {
+    double theta = -acos(D / (4 * r_min)) + atan2(v[1], v[0]);
+    rlr_c[0] = irc[0] + 2 * r_min * cos(theta); rlr_c[1] = irc[1] + 2 * r_min * sin(theta);
+    rlr_rl[0] = (rlr_c[0] + irc[0]) / 2.0; rlr_rl[1] = (rlr_c[1] + irc[1]) / 2.0;
+    rlr_lr[0] = (rlr_c[0] + grc[0]) / 2.0; rlr_lr[1] = (rlr_c[1] + grc[1]) / 2.0;
+    double len = right_turn_dist(il, rlr_rl, irc, r_min) + left_turn_dist(rlr_rl, rlr_lr, rlr_c, r_min) +
+                 right_turn_dist(rlr_lr, gl, grc, r_min);
+    if (best > len) { best = len; type = 2; }
+  }
+  /* l-s-r :436-460 */
+  double lsr1[2] = {0, 0}, lsr2[2] = {0, 0};
+  D = dist2d(grc, ilc);
+  v[0] = (grc[0] - ilc[0]) / D; v[1] = (grc[1] - ilc[1]) / D;
+  R = 2.0 * r_min / D;
+  if (!(fabs(R) > 1)) {
+    double sq = sqrt(1 - R * R);
+    double a = R * v[0] + v[1] * sq, b = R * v[1] - v[0] * sq;
+    lsr1[0] = ilc[0] + a * r_min; lsr2[0] = grc[0] - a * r_min;
+    lsr1[1] = ilc[1] + b * r_min; lsr2[1] = grc[1] - b * r_min;
+    double len = left_turn_dist(il, lsr1, ilc, r_min) + dist2d(lsr2, lsr1) + right_turn_dist(lsr2, gl, grc, r_min);
+    if (best > len) { best = len; type = 3; }
+  }
+  /* l-s-l :463-478 */
+  double lsl1[2], lsl2[2];
+  D = dist2d(glc, ilc);
+  v[0] = (glc[0] - ilc[0]) / D; v[1] = (glc[1] - ilc[1]) / D;
+  lsl1[0] = r_min * v[1] + ilc[0];  lsl2[0] = r_min * v[1] + glc[0];
+  lsl1[1] = -r_min * v[0] + ilc[1]; lsl2[1] = -r_min * v[0] + glc[1];
+  {
+    double len = left_turn_dist(il, lsl1, ilc, r_min) + dist2d(lsl2, lsl1) + left_turn_dist(lsl2, gl, glc, r_min);
+    if (best > len) { best = len; type = 4; }
+  }
+  /* l-r-l :481-499 */
+  double lrl_lr[2] = {NAN, NAN}, lrl_rl[2] = {NAN, NAN}, lrl_c[2] = {NAN, NAN};
+  if (D < 4.0 * r_min) {
+    double theta = acos(D / (4 * r_min)) + atan2(v[1], v[0]);
+    lrl_c[0] = ilc[0] + 2.0 * r_min * cos(theta); lrl_c[1] = ilc[1] + 2.0 * r_min * sin(theta);
+    lrl_lr[0] = (lrl_c[0] + ilc[0]) / 2.0; lrl_lr[1] = (lrl_c[1] + ilc[1]) / 2.0;
+    lrl_rl[0] = (lrl_c[0] + glc[0]) / 2.0; lrl_rl[1] = (lrl_c[1] + glc[1]) / 2.0;
+    double len = left_turn_dist(il, lrl_lr, ilc, r_min) + right_turn_dist(lrl_lr, lrl_rl, lrl_c, r_min) +
+                 left_turn_dist(lrl_rl, gl, glc, r_min);
+    if (best > len) { best = len; type = 5; }
+  }
+  *dist_out = best;
+  *type_out = type;
+  if (type < 0) return 0;
+  static const char *names[6] = {"rsl", "rsr", "rlr", "lsr", "lsl", "lrl"};
+  const char *nm = names[type];
+  const double dphi = .1;
+  int n = 0;
+  /* first part :508-548 */
+  if (nm[0] == 'r') {
+    const double *p = type == 0 ? rsl1 : (type == 1 ? rsr1 : rlr_rl);
+    double ps = atan2(il[1] - irc[1], il[0] - irc[0]), pe = atan2(p[1] - irc[1], p[0] - irc[0]);
+    if (pe > ps) pe = pe - 2.0 * PI;
+    n = emit_arc(irc, r_min, ps, pe, -dphi, traj_xy, n, cap);
+  } else {
+    const double *p = type == 4 ? lsl1 : (type == 3 ? lsr1 : lrl_lr);
+    double ps = atan2(il[1] - ilc[1], il[0] - ilc[0]), pe = atan2(p[1] - ilc[1], p[0] - ilc[0]);
+    if (pe < ps) pe = pe + 2.0 * PI;
+    n = emit_arc(ilc, r_min, ps, pe, dphi, traj_xy, n, cap);
+  }
+  /* second part :552-603 */
+  if (nm[1] == 's') {
+    const double *p1 = type == 3 ? lsr1 : (type == 4 ? lsl1 : (type == 1 ? rsr1 : rsl1));
+    const double *p2 = type == 3 ? lsr2 : (type == 4 ? lsl2 : (type == 1 ? rsr2 : rsl2));
+    if (n < cap) { traj_xy[2 * n] = p1[0]; traj_xy[2 * n + 1] = p1[1]; }
+    n += 1;
+    if (n < cap) { traj_xy[2 * n] = p2[0]; traj_xy[2 * n + 1] = p2[1]; }
+    n += 1;
+  } else if (nm[1] == 'r') { /* lrl */
+    double ps = atan2(lrl_lr[1] - lrl_c[1], lrl_lr[0] - lrl_c[0]), pe = atan2(lrl_rl[1] - lrl_c[1], lrl_rl[0] - lrl_c[0]);
+    if (pe > ps) pe = pe - 2.0 * PI;
+    n = emit_arc(lrl_c, r_min, ps, pe, -dphi, traj_xy, n, cap);
+  } else { /* rlr */
+    double ps = atan2(rlr_rl[1] - rlr_c[1], rlr_rl[0] - rlr_c[0]), pe = atan2(rlr_lr[1] - rlr_c[1], rlr_lr[0] - rlr_c[0]);
+    if (pe < ps) pe = pe + 2.0 * PI;
+    n = emit_arc(rlr_c, r_min, ps, pe, dphi, traj_xy, n, cap);
+  }
+  /* third part :606-655 */
+  if (nm[2] == 'r') {
+    const double *p = type == 1 ? rsr2 : (type == 3 ? lsr2 : rlr_lr);
+    double ps = atan2(p[1] - grc[1], p[0] - grc[0]), pe = atan2(gl[1] - grc[1], gl[0] - grc[0]);
+    if (pe > ps) pe = pe - 2.0 * PI;
+    n = emit_arc(grc, r_min, ps, pe, -dphi, traj_xy, n, cap);
+  } else {
+    const double *p = type == 4 ? lsl2 : (type == 0 ? rsl2 : lrl_rl);
+    double ps = atan2(p[1] - glc[1], p[0] - glc[0]), pe = atan2(gl[1] - glc[1], gl[0] - glc[0]);
+    if (pe < ps) pe = pe + 2.0 * PI;
+    n = emit_arc(glc, r_min, ps, pe, dphi, traj_xy, n, cap);
+  }
+  return n;
+}
+
+/* saturate, DubinsEdge: DRRT_DubinsEdge_functions.jl:70-95 is read below */
+void orc_saturate_dubins(double *new_point, const double *closest, double delta) {
+  const double PI = 3.141592653589793;
+  double this_dist = orc_r3sdist(new_point, closest); /* dist = R3SDist, :41 */
+  if (this_dist > delta) {
+    for (int i = 0; i < 3; ++i) /* :76 */
+      new_point[i] = closest[i] + (new_point[i] - closest[i]) * delta / this_dist;
+    if (fabs(new_point[3] - closest[3]) < PI) { /* :79-81 */
+      new_point[3] = closest[3] + (new_point[3] - closest[3]) * delta / this_dist;
+    } else { /* :82-93 */
+      new_point[3] = (new_point[3] < PI ? new_point[3] + 2 * PI : new_point[3] - 2 * PI);
+      new_point[3] = closest[3] + (new_point[3] - closest[3]) * delta / this_dist;
+      new_point[3] = jl_max(jl_min(new_point[3], 2 * PI), 0.0);
+    }
+  }
+}

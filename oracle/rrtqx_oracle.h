@@ -203,6 +203,15 @@ int orc_edge_check_dubins(const orc_obstacle2d *ob, const double *start_pos,
                           int32_t n_traj, double robot_radius,
                           double min_turn_radius);
 
+/* Dubins calculateTrajectory, space without time (DRRT_DubinsEdge_functions.jl:329-709): six-word
+ * solver + arc discretisation at 0.1 rad.  start4/goal4 = [x y t theta].  type: 0 rsl, 1 rsr, 2 rlr,
+ * 3 lsr, 4 lsl, 5 lrl, -1 none.  Returns the number of trajectory points (x,y rows; written up to
+ * cap).  Uses the C libm, not Julia's: parity with the reference is by tolerance (1e-9), SURVEY A14. */
+int orc_dubins_trajectory(const double *start4, const double *goal4, double r_min, double *dist_out,
+                          int32_t *type_out, double *traj_xy, int32_t cap);
+/* saturate, DubinsEdge (DRRT_DubinsEdge_functions.jl:70-95), in place on new_point[4] */
+void orc_saturate_dubins(double *new_point, const double *closest, double delta);
+
 #ifdef __cplusplus
 }
 #endif
