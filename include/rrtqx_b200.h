@@ -367,6 +367,45 @@ RRTQX_API rrtqx_status rrtqx_dubins_edge_check_batch(
     double robot_radius, double min_turn_radius, uint32_t flags,
     uint8_t *collide_out);
 
+/* ------------------------------------------------ Dubins solver on the device */
+/* calculateTrajectory(S, edge::DubinsEdge), space without time
+ * (DRRT_DubinsEdge_functions.jl:329-709; rightTurnDist / leftTurnDist
+ * DRRT_distance_functions.jl:62-80) for n_edges edges: starts / goals are n x 4
+ * rows [x y t theta] (edge.startNode.position / edge.endNode.position).
+ * Produces per edge: dist (= edge.dist = edge.Wdist = edge.distOriginal; Inf
+ * when no word applies), type (edge.dubinsType: 0 "rsl", 1 "rsr", 2 "rlr",
+ * 3 "lsr", 4 "lsl", 5 "lrl", -1 "xxx") and edge.trajectory[:,1:2] as a CSR
+ * (traj_ptr[n_edges+1], traj_xy n_rows x 2) that can be handed to
+ * rrtqx_dubins_edge_check_batch without leaving the device.
+ * *result may point to NULL (a result object is created) or to a result of an
+ * earlier call (its buffers are reused).  Parity with the reference is by
+ * tolerance (1e-9 relative; Julia libm and twice-precision ranges, SURVEY.md
+ * appendix A14). */
+typedef struct rrtqx_dubins_result rrtqx_dubins_result;
+RRTQX_API rrtqx_status rrtqx_dubins_trajectory_batch(
+    rrtqx_ctx *ctx, const double *starts, const double *goals, int64_t n_edges,
+    double min_turn_radius, rrtqx_dubins_result **result);
+RRTQX_API rrtqx_status rrtqx_dubins_result_destroy(rrtqx_dubins_result *r);
+RRTQX_API rrtqx_status rrtqx_dubins_result_sizes(const rrtqx_dubins_result *r,
+                                                 int64_t *n_edges,
+                                                 int64_t *n_rows);
+/* copies to host or device arrays; any pointer may be NULL */
+RRTQX_API rrtqx_status rrtqx_dubins_result_fetch(rrtqx_dubins_result *r,
+                                                 double *dist, int32_t *type,
+                                                 int64_t *traj_ptr,
+                                                 double *traj_xy);
+/* device views, valid until the next call that reuses the result */
+RRTQX_API rrtqx_status rrtqx_dubins_result_device(
+    const rrtqx_dubins_result *r, const double **dist, const int32_t **type,
+    const int64_t **traj_ptr, const double **traj_xy);
+/* saturate(newPoint, closestPoint, delta), DubinsEdge version
+ * (DRRT_DubinsEdge_functions.jl:70-95, dist = R3SDist
+ * DRRT_distance_functions.jl:41): in place on new_points (n x 4). */
+RRTQX_API rrtqx_status rrtqx_dubins_saturate_batch(rrtqx_ctx *ctx,
+                                                   double *new_points,
+                                                   const double *closest,
+                                                   int64_t n, double delta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -242,3 +242,24 @@ class KDTree:
         dist = np.empty(nq, dtype=np.float64)
         self.L.orc_kd_nearest_batch(self.h, _p(q, c_f64p), 0, nq, _p(idx, c_i32p), _p(dist, c_f64p), nthreads)
         return idx, dist
+
+
+def dubins_trajectory(start4, goal4, r_min, cap=512):
+    """calculateTrajectory(S, edge::DubinsEdge) restated (rrtqx_oracle.c: orc_dubins_trajectory):
+    returns (dist, type, trajectory rows x 2)."""
+    s = np.ascontiguousarray(start4, dtype=np.float64)
+    g = np.ascontiguousarray(goal4, dtype=np.float64)
+    dist = C.c_double(0.0)
+    typ = C.c_int32(0)
+    buf = np.empty((cap, 2), dtype=np.float64)
+    n = lib().orc_dubins_trajectory(_p(s, c_f64p), _p(g, c_f64p), float(r_min), C.byref(dist),
+                                    C.byref(typ), _p(buf, c_f64p), cap)
+    assert n <= cap
+    return dist.value, typ.value, buf[:n].copy()
+
+
+def saturate_dubins(new_point4, closest4, delta):
+    p = np.array(new_point4, dtype=np.float64, copy=True)
+    c = np.ascontiguousarray(closest4, dtype=np.float64)
+    lib().orc_saturate_dubins(_p(p, c_f64p), _p(c, c_f64p), float(delta))
+    return p

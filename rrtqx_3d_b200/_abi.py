@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrtqx_b200.so")
+# RRTQX_B200_LIB: alternative build of the same CUDA library (kernel experiments); never a non-CUDA fallback
+LIB_PATH = os.environ.get("RRTQX_B200_LIB") or os.path.join(_HERE, "librrtqx_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_EMPTY_TREE, ERR_UNSUPPORTED, ERR_STATE = 1, 2, 3, 4, 5, 6
@@ -75,6 +76,12 @@ SIGNATURES = {
     "rrtqx_polygons_upload": (i32, [vp, vp, vp, vp, vp, vp, vp, i64]),
     "rrtqx_segment_check_2d_batch": (i32, [vp, vp, vp, i64, f64, u32, vp]),
     "rrtqx_dubins_edge_check_batch": (i32, [vp, vp, vp, vp, vp, i64, f64, f64, u32, vp]),
+    "rrtqx_dubins_trajectory_batch": (i32, [vp, vp, vp, i64, f64, C.POINTER(vp)]),
+    "rrtqx_dubins_result_destroy": (i32, [vp]),
+    "rrtqx_dubins_result_sizes": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "rrtqx_dubins_result_fetch": (i32, [vp, vp, vp, vp, vp]),
+    "rrtqx_dubins_result_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "rrtqx_dubins_saturate_batch": (i32, [vp, vp, vp, i64, f64]),
 }
 
 _lib = None

@@ -415,6 +415,8 @@ static double host_sqrt_thresh_lt(double r) {
   return t;
 }
 
+#include "range_v5.cuh"
+
 // Kernel variants: more warps per SM when the expected neighbour count is small, bigger hit buffers
 // (fewer warps) when it is large.  Shared memory per block = NW * (2*CAP + FUSED_TAB) * 4 bytes.
 template <int D, int NW, int CAP>
@@ -484,6 +486,7 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
   }
   int variant = k_est <= 576.0 ? 0 : (k_est <= 1280.0 ? 1 : (k_est <= 2048.0 ? 2 : 3));
   if (const char *e = getenv("RRTQX_FUSED_VARIANT")) variant = atoi(e);
+  static const int kernel_gen = [] { const char *e = getenv("RRTQX_RANGE_KERNEL"); return e ? atoi(e) : 5; }();
   unsigned long long total = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     GridView g = t->view();
@@ -494,11 +497,26 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
   launch_fused<D, NW_, CAP_>(ctx, g, dq, res->qbins > 0 ? res->qsorted.p : nullptr, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
                              want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,             \
                              count_only ? 0 : 1)
+#define RQ_V5(NW_, CAP_, TAB_)                                                                                       \
+  launch_v5<D, NW_, CAP_, TAB_>(ctx, g, dq, res->qbins > 0 ? res->qsorted.p : nullptr, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
+                                want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p, count_only ? 0 : 1)
+      if (kernel_gen >= 5) {
+        // v5 (FP32 filter scan, packed exact records, 16-bit hit codes): hit buffers leave 32*V5_U entries of
+        // head-room; the octet table must hold a whole pair's region (else the pair takes the exact routine)
+        static const int v5_nw = [] { const char *e = getenv("RRTQX_V5_NW"); return e ? atoi(e) : 24; }();
+        if (variant == 0 && v5_nw == 28) RQ_V5(28, 704, 256);
+        else if (variant == 0 && v5_nw == 20) RQ_V5(20, 704, 256);
+        else if (variant == 0) RQ_V5(24, 704, 256);     // 24 warps/SM (80 registers), 94 KB shared
+        else if (variant == 1) RQ_V5(24, 1408, 512);    // 186 KB
+        else if (variant == 2) RQ_V5(16, 2176, 1024);   // 205 KB
+        else RQ_V5(8, 4224, 2048);                      // 201 KB
+      } else
       if (variant == 0) RQ_FUSED(28, 576);        // 28 warps/SM (72 registers), 158 KB shared; measured best of 20/24/28/32
       else if (variant == 1) RQ_FUSED(20, 1280);  // 20 warps/SM, 225 KB
       else if (variant == 2) RQ_FUSED(12, 2048);  // 12 warps/SM, 209 KB
       else RQ_FUSED(6, 4096);                     //  6 warps/SM, 203 KB: up to 4096 neighbours buffered per query
 #undef RQ_FUSED
+#undef RQ_V5
     }
     RQ_CUDA(cudaMemcpyAsync(&total, res->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, st));
     RQ_CUDA(cudaStreamSynchronize(st));

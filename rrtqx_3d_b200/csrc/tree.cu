@@ -238,17 +238,40 @@ __global__ void cell_sort_kernel(const int32_t *__restrict__ cell_start, int nce
   }
 }
 
-__global__ void cell_gather_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ sperm, int64_t n,
+// Also writes the two per-slot records of the v5 range kernel: the FP32 filter record (coordinates
+// relative to the grid origin, so the rounding error is bounded by 2^-24 * extent) and the exact
+// FP64 record, and accumulates max |component| of the filter records (bit pattern order of
+// non-negative floats; a NaN/Inf component yields a non-finite maximum, which disables the filter).
+__global__ void cell_gather_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ sperm, int64_t n, int d,
+                                   double lox, double loy, double loz,
                                    double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz,
-                                   double *__restrict__ sw) {
+                                   double *__restrict__ sw, float4 *__restrict__ f4, double4 *__restrict__ d4,
+                                   float *__restrict__ fmaxabs) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int node = sperm[j];
-  double4 p = pos[node];
-  sx[j] = p.x;
-  sy[j] = p.y;
-  sz[j] = p.z;
-  sw[j] = p.w;
+  float m = 0.0f;
+  if (j < n) {
+    const int node = sperm[j];
+    double4 p = pos[node];
+    sx[j] = p.x;
+    sy[j] = p.y;
+    sz[j] = p.z;
+    sw[j] = p.w;
+    float4 f;
+    f.x = __double2float_rn(__dsub_rn(p.x, lox));
+    f.y = __double2float_rn(__dsub_rn(p.y, loy));
+    f.z = __double2float_rn(__dsub_rn(p.z, loz));
+    f.w = __double2float_rn(p.w);
+    f4[j] = f;
+    double4 r = p;
+    if (d <= 3) r.w = __longlong_as_double((long long)(unsigned)node);
+    d4[j] = r;
+    // NaN components never produce a hit (neither in FP32 nor in FP64) and are skipped by fmaxf;
+    // infinities make the maximum infinite.
+    m = fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax((int *)fmaxabs, __float_as_int(m));
 }
 
 void tree_reindex(rrtqx_tree *t) {
@@ -328,6 +351,10 @@ void tree_reindex(rrtqx_tree *t) {
   t->sy.ensure((size_t)n + 8, st);
   t->sz.ensure((size_t)n + 8, st);
   t->sw.ensure((size_t)n + 8, st);
+  t->f4.ensure((size_t)n + 8, st);
+  t->d4.ensure((size_t)n + 8, st);
+  t->fmaxabs.ensure(1, st);
+  RQ_CUDA(cudaMemsetAsync(t->fmaxabs.p, 0, sizeof(float), st));
   RQ_CUDA(cudaMemsetAsync(t->cell_cursor.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   t->n_sorted = n;  // view() below must describe the new grid
   GridView g = t->view();
@@ -338,7 +365,8 @@ void tree_reindex(rrtqx_tree *t) {
   RQ_CUDA(cudaMemsetAsync(t->cell_cursor.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   cell_scatter_kernel<<<div_up(n, TB), TB, 0, st>>>(t->cell_id.p, n, t->cell_start.p, t->cell_cursor.p, t->sperm.p);
   cell_sort_kernel<<<div_up(ncell, TB), TB, 0, st>>>(t->cell_start.p, ncell, t->sperm.p);
-  cell_gather_kernel<<<div_up(n, TB), TB, 0, st>>>(t->pos.p, t->sperm.p, n, t->sx.p, t->sy.p, t->sz.p, t->sw.p);
+  cell_gather_kernel<<<div_up(n, TB), TB, 0, st>>>(t->pos.p, t->sperm.p, n, t->d, t->lo[0], t->lo[1], t->lo[2], t->sx.p, t->sy.p,
+                                                   t->sz.p, t->sw.p, t->f4.p, t->d4.p, t->fmaxabs.p);
   post_launch(ctx, 3);
 }
 

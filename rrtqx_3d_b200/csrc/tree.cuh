@@ -38,6 +38,10 @@ struct GridView {
   const double *sx, *sy, *sz, *sw;
   const int *sperm;        // sorted slot -> node index
   const double4 *pos;      // node index -> (x,y,z,w)
+  // records of the v5 range kernel (range_v5.cuh)
+  const float4 *f4;        // slot -> FP32 filter record ((x,y,z) - lo, w), round-to-nearest
+  const double4 *d4;       // slot -> exact record (x, y, z, w); for d <= 3 the low word of .w holds the node index
+  const float *fmaxabs;    // device scalar: max |component| over all f4 records (error bound of the FP32 filter)
 };
 
 #ifdef __CUDACC__
@@ -76,6 +80,9 @@ struct rrtqx_tree {
   double lo[3] = {0, 0, 0}, inv[3] = {1, 1, 1}, cell[3] = {1, 1, 1};
   rrtqx::DevBuf<int32_t> cell_start, cell_cursor, cell_id, sperm;
   rrtqx::DevBuf<double> sx, sy, sz, sw;
+  rrtqx::DevBuf<float4> f4;
+  rrtqx::DevBuf<double4> d4;
+  rrtqx::DevBuf<float> fmaxabs;
   rrtqx::DevBuf<double> bbox_partial;
   rrtqx::DevBuf<int32_t> scan_tmp;
 
@@ -90,6 +97,7 @@ struct rrtqx_tree {
     g.sx = sx.p; g.sy = sy.p; g.sz = sz.p; g.sw = sw.p;
     g.sperm = sperm.p;
     g.pos = pos.p;
+    g.f4 = f4.p; g.d4 = d4.p; g.fmaxabs = fmaxabs.p;
     return g;
   }
 };

@@ -458,3 +458,67 @@ def dubins_edge_check_batch(polys: PolygonSet, starts, ends, traj_ptr, traj_xy, 
                                                   A.ptr(traj_xy) if len(traj_xy) else None, n, float(robot_radius),
                                                   float(min_turn_radius), int(flags), A.ptr(out)), polys.ctx.h)
     return out
+
+
+class DubinsResult:
+    """rrtqx_dubins_result: per-edge dist / dubinsType and edge.trajectory[:,1:2] rows as a CSR, device resident."""
+    TYPES = ("rsl", "rsr", "rlr", "lsr", "lsl", "lrl")  # edge.dubinsType; -1 is the reference's "xxx"
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.h = A.vp()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_dubins_result_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sizes(self):
+        ne, nr = A.i64(), A.i64()
+        A.check(self.L.rrtqx_dubins_result_sizes(self.h, C.byref(ne), C.byref(nr)), self.ctx.h)
+        return ne.value, nr.value
+
+    def fetch(self):
+        """(dist[n], type[n], traj_ptr[n+1], traj_xy[rows, 2]) as numpy arrays."""
+        ne, nr = self.sizes()
+        dist = np.empty(ne, dtype=np.float64)
+        typ = np.empty(ne, dtype=np.int32)
+        ptr = np.zeros(ne + 1, dtype=np.int64)
+        xy = np.empty((nr, 2), dtype=np.float64)
+        A.check(self.L.rrtqx_dubins_result_fetch(self.h, A.ptr(dist), A.ptr(typ), A.ptr(ptr), A.ptr(xy) if nr else None),
+                self.ctx.h)
+        return dist, typ, ptr, xy
+
+    def device_pointers(self):
+        d, t, p, x = A.vp(), A.vp(), A.vp(), A.vp()
+        A.check(self.L.rrtqx_dubins_result_device(self.h, C.byref(d), C.byref(t), C.byref(p), C.byref(x)), self.ctx.h)
+        return d.value, t.value, p.value, x.value
+
+
+def dubins_trajectory_batch(ctx: Context, starts, goals, min_turn_radius, result: DubinsResult | None = None, n_edges=None):
+    """calculateTrajectory(S, edge::DubinsEdge) for a batch: starts / goals are n x 4 rows [x y t theta]
+    (numpy, or raw device pointers with n_edges given)."""
+    if result is None:
+        result = DubinsResult(ctx)
+    if isinstance(starts, (int, np.integer)):
+        n, ps, pg = int(n_edges), int(starts), int(goals)
+    else:
+        starts, goals = A.as_f64(starts, 4), A.as_f64(goals, 4)
+        n, ps, pg = starts.shape[0], A.ptr(starts), A.ptr(goals)
+    A.check(ctx.L.rrtqx_dubins_trajectory_batch(ctx.h, ps, pg, n, float(min_turn_radius), C.byref(result.h)), ctx.h)
+    return result
+
+
+def dubins_saturate_batch(ctx: Context, new_points, closest, delta):
+    """saturate(newPoint, closestPoint, delta), DubinsEdge version, in place on a copy; returns the n x 4 array."""
+    pts = np.array(A.as_f64(new_points, 4), copy=True)
+    cl = A.as_f64(closest, 4)
+    A.check(ctx.L.rrtqx_dubins_saturate_batch(ctx.h, A.ptr(pts), A.ptr(cl), pts.shape[0], float(delta)), ctx.h)
+    return pts
