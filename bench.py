@@ -30,6 +30,10 @@ if ROOT not in sys.path:
 
 from rrtqx_3d_b200 import workloads as W  # noqa: E402
 
+# the kernel the library launches for C2 (RRTQX_RANGE_KERNEL=4 selects the previous generation for A/B runs)
+DOMINANT_KERNEL = ("range_fused_kernel<3,2,28,576>" if os.environ.get("RRTQX_RANGE_KERNEL") == "4"
+                   else "range_v5_kernel<3,24,704,256,uniform>")
+
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -157,7 +161,18 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_C3_CACHE = {}
+
+
 def build_c3_edges(tree, pts, r_edge):
+    """Memoised per process (the sweep and the C5 leg use the same edge set)."""
+    key = (id(tree), float(r_edge))
+    if key not in _C3_CACHE:
+        _C3_CACHE[key] = _build_c3_edges(tree, pts, r_edge)
+    return _C3_CACHE[key]
+
+
+def _build_c3_edges(tree, pts, r_edge):
     """C3 edge set: all ordered pairs (i, j), i != j, within r_edge, generated with the range kernel;
     parent[i] = lowest-index neighbour below i, else the node's kd parent (always a lower index)."""
     res, total = tree.range_query(pts, r_edge, want_dist=False)
@@ -167,7 +182,10 @@ def build_c3_edges(tree, pts, r_edge):
     src = np.empty(total, dtype=np.int32)
     src[:] = np.repeat(order.astype(np.int32), counts[order])     # lists are packed in offset order
     keep = src != idx
-    src, dst = np.ascontiguousarray(src[keep]), np.ascontiguousarray(idx[keep])
+    src, dst = src[keep], idx[keep]
+    # canonical order (the kernel's list order depends on its atomics): every rank shards the SAME array
+    order = np.argsort(src.astype(np.int64) << 32 | dst.astype(np.int64), kind="stable")
+    src, dst = np.ascontiguousarray(src[order]), np.ascontiguousarray(dst[order])
     parent = tree.kd_fields()[0].copy()
     lower = dst < src
     cand = np.full(len(pts), np.iinfo(np.int32).max, dtype=np.int32)
@@ -249,6 +267,96 @@ def c1_replay(ctx, n_iter):
             "note": "latency-bound: one launch + one stream synchronise per iteration, results via mapped pinned memory"}
 
 
+def c4_dubins(ctx, n_edges, steps):
+    """Config C4: Dubins edges between poses in [-50,50]^2 x [0,2pi): the six-word solver + trajectory
+    discretisation on the device, then the sampled-trajectory collision check against 100 city-block polygons,
+    trajectories never leaving the GPU.  CPU: the oracle's solver + check on a bounded sample, one thread."""
+    import ctypes as C
+
+    import oracle
+    import torch
+    from rrtqx_3d_b200 import _abi as A
+    from rrtqx_3d_b200.device import DubinsResult, PolygonSet, dubins_trajectory_batch
+    u = W.uniform01(44, 0, 6 * n_edges).reshape(n_edges, 6)
+    s = np.zeros((n_edges, 4))
+    s[:, 0], s[:, 1], s[:, 3] = -50 + 100 * u[:, 0], -50 + 100 * u[:, 1], 2 * np.pi * u[:, 2]
+    ang, rad = 2 * np.pi * u[:, 3], 4.0 * np.sqrt(u[:, 4])
+    g = np.zeros((n_edges, 4))
+    g[:, 0], g[:, 1], g[:, 3] = s[:, 0] + rad * np.cos(ang), s[:, 1] + rad * np.sin(ang), 2 * np.pi * u[:, 5]
+    P = PolygonSet(ctx)
+    P.upload(W.c4_city_blocks())
+    ds, dg = torch.from_numpy(s).cuda(), torch.from_numpy(g).cuda()
+    s2, g2 = torch.from_numpy(np.ascontiguousarray(s[:, :2])).cuda(), torch.from_numpy(np.ascontiguousarray(g[:, :2])).cuda()
+    out = torch.empty(n_edges, dtype=torch.uint8, device="cuda")
+    res = DubinsResult(ctx)
+    t_solve, t_check = [], []
+    for it in range(3 + steps):
+        dubins_trajectory_batch(ctx, ds.data_ptr(), dg.data_ptr(), 1.0, result=res, n_edges=n_edges)
+        _, _, dptr, dxy = res.device_pointers()
+        A.check(ctx.L.rrtqx_dubins_edge_check_batch(P.h, s2.data_ptr(), g2.data_ptr(), dptr, dxy, n_edges, 0.5, 1.0, 0,
+                                                    out.data_ptr()), ctx.h)
+        if it >= 3:
+            t_solve.append(ctx.last_phase_ms("dubins_solve") + ctx.last_phase_ms("dubins_emit"))
+            t_check.append(ctx.last_phase_ms("dubins_check"))
+    _, rows = res.sizes()
+    ms_s, ms_c = float(np.mean(t_solve)), float(np.mean(t_check))
+    # CPU sample
+    L = oracle.lib()
+    f = lambda a: oracle._p(np.ascontiguousarray(a, dtype=np.float64), oracle.c_f64p)
+    obs = []
+    for i in range(len(P.kind)):
+        ob = oracle.Obstacle2D()
+        ob.kind = int(P.kind[i])
+        ob.pos[0], ob.pos[1] = P.centers[i]
+        ob.radius, ob.life_span, ob.unused = P.radii[i], float("inf"), 0
+        v = np.ascontiguousarray(P.verts[P.vptr[i]:P.vptr[i + 1]])
+        ob.n_vert, ob._keep, ob.poly = len(v), v, oracle._p(v, oracle.c_f64p)
+        obs.append(ob)
+    n_cpu = min(n_edges, 3000)
+    t0 = time.perf_counter()
+    hits = 0
+    for e in range(n_cpu):
+        _, _, traj = oracle.dubins_trajectory(s[e], g[e], 1.0)
+        for ob in obs:
+            if L.orc_edge_check_dubins(C.byref(ob), f(s[e, :2]), f(g[e, :2]), f(traj), len(traj), 0.5, 1.0):
+                hits += 1
+                break
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "C4 Dubins edges (r_turn 1, r_robot 0.5) vs 100 city-block polygons: device solver + "
+                        "trajectory discretisation + sampled-trajectory collision check",
+            "edges": n_edges, "trajectory_rows": rows, "solve_ms": ms_s, "check_ms": ms_c,
+            "edges_per_s": n_edges / ((ms_s + ms_c) / 1e3), "colliding_edges": int(out.sum().item()),
+            "cpu_edges_per_s": n_cpu / cpu_s, "cpu": f"oracle solver + check, 1 thread, first {n_cpu} edges "
+                                                    "(python call overhead included)",
+            "algorithmic_bytes": n_edges * (64 + 16 + 1) + rows * 16 * 2}
+
+
+def c5_instances(ctx, rank, world, n_instances, n_iter):
+    """Config C5a: independent C1-style planning instances (seeds 1..n), round-robin over ranks; each instance is
+    the incremental loop extend_query + insert.  Returns (iterations done by this rank, seconds)."""
+    from rrtqx_3d_b200 import _abi as A
+    from rrtqx_3d_b200.device import DeviceTree, SphereSet, extend_query
+    centers, radii, _ = W.building2_spheres()
+    S = SphereSet(ctx, centers, radii)
+    bufs = (np.empty(8192, np.int32), np.empty(8192, np.float64), np.empty(8192, np.uint8), np.empty(8192, np.uint8))
+    done = 0
+    t0 = time.perf_counter()
+    for inst in range(rank, n_instances, world):
+        samples = W.uniform_points(1 + inst, n_iter, [-W.ENV_RAD] * 3, [W.ENV_RAD] * 3)
+        t = DeviceTree(ctx, 3)
+        t.insert(np.array([4.0, 16.5, -7.5]))
+        n = 1
+        for it in range(n_iter):
+            r = W.shrinking_ball_radius(n, 3, W.DELTA, W.BALL_CONSTANT)
+            res = extend_query(t, S, samples[it], r, W.ROBOT_RADIUS, A.CHECK_QUICK_PASS, capacity=8192, bufs=bufs)
+            if not res.point_collides:
+                t.insert(samples[it])
+                n += 1
+        done += n_iter
+        t.close()
+    return done, time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,6 +374,11 @@ def main():
     ap.add_argument("--c1-iterations", type=int, default=20000)
     ap.add_argument("--sweep-edge-radius", type=float, default=0.5346)
     ap.add_argument("--sweep-obstacles", type=int, default=256)
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--c4-edges", type=int, default=200_000)
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--c5-instances", type=int, default=64)
+    ap.add_argument("--c5-iterations", type=int, default=1000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -369,7 +482,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
                 "note": "achieved = compulsory bytes of the whole range-query step / CUDA-event time of the step "
-                        "(query sort + fused single-pass kernel); dominant kernel = range_fused_kernel<3,2,24>",
+                        "(query sort + fused single-pass kernel); dominant kernel = " + DOMINANT_KERNEL,
                 "kernel_ms": kern_ms, "dominant_kernel_share": fill_share,
                 "dominant_kernel_frac": alg_bytes / (kern_ms["range_fill"] / 1e3) / 1e9 / peak_gbs}
 
@@ -480,6 +593,60 @@ def main():
                                   "algorithmic_bytes": sbytes, "hbm_frac": sbytes / (sms / 1e3) / 1e9 / peak_gbs}
         except Exception as exc:  # the headline line must still be printed
             line["edge_sweep"] = {"error": repr(exc)}
+
+    # ------------------------------------------------- C5: sharded edge-check batch + independent instances
+    if not args.no_c5:
+        try:
+            from rrtqx_3d_b200.device import edge_check_batch
+            from rrtqx_3d_b200.sharding import shard_bounds
+            src, dst, _ = build_c3_edges(tree, pts, args.sweep_edge_radius)     # every rank: same edge set
+            centers, radii = W.c3_obstacles(args.sweep_obstacles)
+            S5 = SphereSet(ctx, centers, radii)
+            lo, hi = shard_bounds(len(src), rank, world)
+            per = (len(src) + world - 1) // world
+            dsrc, ddst = torch.from_numpy(src[lo:hi]).cuda(), torch.from_numpy(dst[lo:hi]).cuda()
+            dflag = torch.zeros(per, dtype=torch.uint8, device="cuda")           # padded to a common shard size
+            allflags = torch.empty(per * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+            evs = []
+            for it in range(3 + args.steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if world > 1:
+                    dist.barrier()
+                a.record(stream)
+                edge_check_batch(tree, S5, dsrc, ddst, W.ROBOT_RADIUS, n_edges=hi - lo, out=dflag)
+                if world > 1:   # the only exchange of the path: gather the sharded flags (NCCL)
+                    dist.all_gather_into_tensor(allflags, dflag)
+                b.record(stream)
+                b.synchronize()
+                if it >= 3:
+                    evs.append(a.elapsed_time(b))
+            ems = float(np.mean(evs))
+            done, secs = c5_instances(ctx, rank, world, args.c5_instances, args.c5_iterations)
+            if world > 1:
+                tt = torch.tensor([ems, secs], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ems, secs = float(tt[0].item()), float(tt[1].item())
+                dd = torch.tensor([done], device="cuda", dtype=torch.int64)
+                dist.all_reduce(dd)
+                done = int(dd.item())
+                colliding = int(allflags.view(world, per)[:, :].sum().item())
+            else:
+                colliding = int(dflag.sum().item())
+            line["c5"] = {"workload": "C5: C3 edge set sharded contiguously over the ranks (tree + 256 spheres replicated, "
+                                      "flags all-gathered over NCCL) and independent C1-style planning instances round-robin",
+                          "edges": len(src), "edge_shards": world, "edge_batch_ms": ems,
+                          "edges_per_s": len(src) / (ems / 1e3), "colliding_edges": colliding, "scaling": "strong",
+                          "instances": args.c5_instances, "iterations_per_instance": args.c5_iterations,
+                          "instance_seconds": secs, "planner_iterations_per_s": done / secs}
+        except Exception as exc:
+            line["c5"] = {"error": repr(exc)}
+
+    if not args.no_c4 and rank == 0 and world == 1:
+        try:
+            line["dubins"] = c4_dubins(ctx, args.c4_edges, max(3, min(args.steps, 10)))
+        except Exception as exc:
+            line["dubins"] = {"error": repr(exc)}
 
     if not args.no_c1 and rank == 0 and world == 1:
         try:
