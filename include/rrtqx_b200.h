@@ -272,6 +272,19 @@ RRTQX_API rrtqx_status rrtqx_edges_upload(rrtqx_edges *e, const int32_t *src,
                                           const int32_t *dst, int64_t n_edges,
                                           const int32_t *parent,
                                           int64_t n_parent);
+/* Neighbour-graph residency.  rrtqx_edges_append adds n_new edges behind the existing ones
+ * (edge id = position, continuing the upload order): the edges the planner creates in one iteration
+ * (makeNeighborOf / makeInitialOutNeighborOf, DRRT_Q.jl:2589-2593); endpoints may be nodes inserted into the
+ * tree since the upload.  rrtqx_edges_set_parents re-points parent edges (makeParentOf, DRRT_Q.jl:1841-1856):
+ * parent_ids[i] becomes the parent of node_ids[i], -1 = rrtParentUsed false; nodes never mentioned have no
+ * parent edge.  Neither call re-uploads the graph; the device CSR is rebuilt before the next sweep.  Edges
+ * are never deleted: results for edges the planner has culled are ignored by the caller. */
+RRTQX_API rrtqx_status rrtqx_edges_append(rrtqx_edges *e, const int32_t *src,
+                                          const int32_t *dst, int64_t n_new);
+RRTQX_API rrtqx_status rrtqx_edges_set_parents(rrtqx_edges *e,
+                                               const int32_t *node_ids,
+                                               const int32_t *parent_ids,
+                                               int64_t n);
 RRTQX_API rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges);
 
 /* addNewObstacle (DRRT_Q.jl:3220-3290) geometric part, batched over obstacles

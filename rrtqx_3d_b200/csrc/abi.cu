@@ -511,6 +511,25 @@ rrtqx_status rrtqx_edges_upload(rrtqx_edges *e, const int32_t *src, const int32_
   });
 }
 
+rrtqx_status rrtqx_edges_append(rrtqx_edges *e, const int32_t *src, const int32_t *dst, int64_t n_new) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(n_new == 0 || (src && dst), "src / dst is NULL");
+    edges_append(e, src, dst, n_new);
+  });
+}
+
+rrtqx_status rrtqx_edges_set_parents(rrtqx_edges *e, const int32_t *node_ids, const int32_t *parent_ids, int64_t n) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    edges_set_parents(e, node_ids, parent_ids, n);
+  });
+}
+
 rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges) {
   if (!e || !n_edges) return RRTQX_ERR_INVALID;
   *n_edges = e->n_edges;

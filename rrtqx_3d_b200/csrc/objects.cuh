@@ -30,6 +30,8 @@ struct rrtqx_edges {
   int64_t n_edges = 0;
   int64_t n_nodes = 0;  // tree size at upload
   bool has_parent = false;
+  bool dirty = false;   // appended edges / parent updates not yet in the CSR
+  int64_t n_parent = 0; // entries of parent[] that are initialised
   rrtqx::DevBuf<int32_t> src, dst;            // upload order (edge id = position)
   rrtqx::DevBuf<int32_t> row_ptr, cursor;     // CSR by start node
   rrtqx::DevBuf<int32_t> csr_dst, csr_eid;
@@ -77,6 +79,9 @@ void node_check(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *poin
 // sweep.cu
 void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
                   int64_t n_parent);
+void edges_append(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t n_new);
+void edges_set_parents(rrtqx_edges *E, const int32_t *nodes, const int32_t *parents, int64_t n);
+void edges_rebuild(rrtqx_edges *E);
 void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *ob_ids, int64_t n_obs,
                         double robot_radius, double delta, uint32_t flags, rrtqx_sweep_result *R);
 void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id, const int32_t *other_ids,

@@ -56,37 +56,26 @@ __global__ void edge_rows_kernel(const double4 *__restrict__ pos, const int32_t 
   degenerate[v] = degen ? 1 : 0;
 }
 
-void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
-                  int64_t n_parent) {
+// (Re)build the CSR by start node and the per-node cull data from the resident src / dst / parent arrays for
+// the CURRENT tree size.  Runs on the device; called lazily by the sweeps after appends / parent updates.
+void edges_rebuild(rrtqx_edges *E) {
   rrtqx_tree *t = E->tree;
   rrtqx_ctx *ctx = t->ctx;
   cudaStream_t st = ctx->stream;
-  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
-  RQ_REQUIRE(ne >= 0 && ne < (int64_t)0x7fffffff, "n_edges out of range");
-  const int64_t nn = t->n;
-  RQ_REQUIRE(parent == nullptr || n_parent == nn, "parent array must have one entry per tree node");
-  E->n_edges = ne;
-  E->n_nodes = nn;
-  E->has_parent = parent != nullptr;
-  E->src.ensure((size_t)ne + 1, st);
-  E->dst.ensure((size_t)ne + 1, st);
+  const int64_t ne = E->n_edges, nn = t->n;
+  RQ_REQUIRE(nn >= E->n_nodes, "the tree shrank under a resident edge set");
   E->csr_dst.ensure((size_t)ne + 1, st);
   E->csr_eid.ensure((size_t)ne + 1, st);
   E->row_ptr.ensure((size_t)nn + 2, st);
   E->cursor.ensure((size_t)nn + 2, st);
-  E->parent.ensure((size_t)nn + 1, st);
   E->lmax.ensure((size_t)nn + 1, st);
   E->degenerate.ensure((size_t)nn + 1, st);
-  if (ne) {
-    RQ_CUDA(cudaMemcpyAsync(E->src.p, src, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
-    RQ_CUDA(cudaMemcpyAsync(E->dst.p, dst, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
+  if (E->has_parent && nn > E->n_parent) {  // nodes inserted since the last parent update: no parent edge yet
+    E->parent.ensure((size_t)nn + 1, st, (size_t)E->n_parent);
+    RQ_CUDA(cudaMemsetAsync(E->parent.p + E->n_parent, 0xff, sizeof(int32_t) * (size_t)(nn - E->n_parent), st));
+    E->n_parent = nn;
   }
-  if (parent) RQ_CUDA(cudaMemcpyAsync(E->parent.p, parent, sizeof(int32_t) * nn, cudaMemcpyDefault, st));
-  // validate indices on the host side only when the arrays are host arrays
-  if (ne && !is_device_ptr(src)) {
-    for (int64_t e = 0; e < ne; ++e)
-      RQ_REQUIRE(src[e] >= 0 && src[e] < nn && dst[e] >= 0 && dst[e] < nn, "edge endpoint out of range");
-  }
+  E->n_nodes = nn;
   const int TB = 256;
   RQ_CUDA(cudaMemsetAsync(E->cursor.p, 0, sizeof(int32_t) * ((size_t)nn + 1), st));
   if (ne) { edge_hist_kernel<<<div_up(ne, TB), TB, 0, st>>>(E->src.p, ne, E->cursor.p); post_launch(ctx); }
@@ -98,10 +87,104 @@ void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
   }
   if (nn) {
     edge_rows_kernel<<<div_up(nn, TB), TB, 0, st>>>(t->pos.p, E->dst.p, E->row_ptr.p, E->csr_eid.p, E->csr_dst.p,
-                                                    parent ? E->parent.p : nullptr, nn, E->lmax.p, E->degenerate.p);
+                                                    E->has_parent ? E->parent.p : nullptr, nn, E->lmax.p, E->degenerate.p);
     post_launch(ctx);
   }
+  E->dirty = false;
+}
+
+static void validate_endpoints(const int32_t *src, const int32_t *dst, int64_t ne, int64_t nn) {
+  // indices are validated on the host side only when the arrays are host arrays
+  if (ne && !is_device_ptr(src))
+    for (int64_t e = 0; e < ne; ++e)
+      RQ_REQUIRE(src[e] >= 0 && src[e] < nn && dst[e] >= 0 && dst[e] < nn, "edge endpoint out of range");
+}
+
+void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
+                  int64_t n_parent) {
+  rrtqx_tree *t = E->tree;
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
+  RQ_REQUIRE(ne >= 0 && ne < (int64_t)0x7fffffff, "n_edges out of range");
+  const int64_t nn = t->n;
+  RQ_REQUIRE(parent == nullptr || n_parent == nn, "parent array must have one entry per tree node");
+  validate_endpoints(src, dst, ne, nn);
+  E->n_edges = ne;
+  E->n_nodes = 0;
+  E->has_parent = parent != nullptr;
+  E->n_parent = parent ? nn : 0;
+  E->src.ensure((size_t)ne + 1, st);
+  E->dst.ensure((size_t)ne + 1, st);
+  E->parent.ensure((size_t)nn + 1, st);
+  if (ne) {
+    RQ_CUDA(cudaMemcpyAsync(E->src.p, src, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
+    RQ_CUDA(cudaMemcpyAsync(E->dst.p, dst, sizeof(int32_t) * ne, cudaMemcpyDefault, st));
+  }
+  if (parent) RQ_CUDA(cudaMemcpyAsync(E->parent.p, parent, sizeof(int32_t) * nn, cudaMemcpyDefault, st));
+  edges_rebuild(E);
   RQ_CUDA(cudaStreamSynchronize(st));
+}
+
+// Neighbour-graph residency: the planner appends the edges it creates per iteration
+// (makeNeighborOf / makeInitialOutNeighborOf, DRRT_Q.jl:2589-2593; edge id = position, continuing the upload
+// order) and re-points parent edges (makeParentOf :1841-1856) without re-uploading the graph.  The CSR is
+// rebuilt on the device before the next sweep.
+void edges_append(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t n_new) {
+  rrtqx_tree *t = E->tree;
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
+  RQ_REQUIRE(n_new >= 0 && E->n_edges + n_new < (int64_t)0x7fffffff, "n_edges out of range");
+  if (n_new == 0) return;
+  validate_endpoints(src, dst, n_new, t->n);
+  const size_t old = (size_t)E->n_edges;
+  E->src.ensure(old + (size_t)n_new + 1, st, old);
+  E->dst.ensure(old + (size_t)n_new + 1, st, old);
+  RQ_CUDA(cudaMemcpyAsync(E->src.p + old, src, sizeof(int32_t) * n_new, cudaMemcpyDefault, st));
+  RQ_CUDA(cudaMemcpyAsync(E->dst.p + old, dst, sizeof(int32_t) * n_new, cudaMemcpyDefault, st));
+  E->n_edges += n_new;
+  E->dirty = true;
+  RQ_CUDA(cudaStreamSynchronize(st));  // the caller's arrays may be reused on return
+}
+
+__global__ void parent_scatter_kernel(const int32_t *__restrict__ nodes, const int32_t *__restrict__ parents, int64_t n,
+                                      int64_t n_nodes, int32_t *__restrict__ parent, int32_t *__restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = nodes[i], p = parents[i];
+  if (v < 0 || v >= n_nodes || p < -1 || p >= n_nodes) { atomicAdd(bad, 1); return; }
+  parent[v] = p;  // -1: rrtParentUsed = false
+}
+
+void edges_set_parents(rrtqx_edges *E, const int32_t *nodes, const int32_t *parents, int64_t n) {
+  rrtqx_tree *t = E->tree;
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(n >= 0 && (n == 0 || (nodes && parents)), "bad arguments");
+  const int64_t nn = t->n;
+  if (!E->has_parent) {  // first parent information: every node starts without a parent edge
+    E->parent.ensure((size_t)nn + 1, st);
+    RQ_CUDA(cudaMemsetAsync(E->parent.p, 0xff, sizeof(int32_t) * ((size_t)nn + 1), st));
+    E->has_parent = true;
+    E->n_parent = nn;
+  } else if (nn > E->n_parent) {
+    E->parent.ensure((size_t)nn + 1, st, (size_t)E->n_parent);
+    RQ_CUDA(cudaMemsetAsync(E->parent.p + E->n_parent, 0xff, sizeof(int32_t) * (size_t)(nn - E->n_parent), st));
+    E->n_parent = nn;
+  }
+  if (n == 0) return;
+  const int32_t *dn = to_device(ctx, nodes, (size_t)n, ctx->stage_i32a);
+  const int32_t *dp = to_device(ctx, parents, (size_t)n, ctx->stage_i32b);
+  t->flagbuf.ensure(8, st);
+  RQ_CUDA(cudaMemsetAsync(t->flagbuf.p, 0, sizeof(int32_t), st));
+  parent_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(dn, dp, n, nn, E->parent.p, t->flagbuf.p);
+  post_launch(ctx);
+  int32_t bad = 0;
+  RQ_CUDA(cudaMemcpyAsync(&bad, t->flagbuf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaStreamSynchronize(st));
+  E->dirty = true;
+  RQ_REQUIRE(bad == 0, "node / parent index out of range");
 }
 
 // ------------------------------------------------------ sweep obstacle table
@@ -394,6 +477,7 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
   if (!is_device_ptr(ob_ids))
     for (int64_t i = 0; i < n_obs; ++i) RQ_REQUIRE(ob_ids[i] >= 0 && ob_ids[i] < S->n, "obstacle id out of range");
   const int32_t *dids = to_device(ctx, ob_ids, (size_t)n_obs, R->ids_stage);
+  if (E->dirty || E->tree->n != E->n_nodes) edges_rebuild(E);  // appended edges / parents / new nodes
   PhaseScope ph(ctx, "add_sweep");
   prepare_result(E, R);
   bool no_stats = false;
@@ -452,6 +536,7 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
   RQ_REQUIRE(ob_id >= 0 && ob_id < S->n, "obstacle id out of range");
   RQ_REQUIRE(n_others >= 0 && n_others < (1 << 24), "n_others out of range");
   RQ_REQUIRE(edge_dist_inf != nullptr || E->n_edges == 0, "edge_dist_inf is NULL");
+  if (E->dirty || E->tree->n != E->n_nodes) edges_rebuild(E);
   // table = [ob_id, others...]
   std::vector<int32_t> ids((size_t)n_others + 1);
   ids[0] = ob_id;

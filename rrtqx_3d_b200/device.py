@@ -337,6 +337,16 @@ class EdgeSet:
         A.check(self.L.rrtqx_edges_upload(self.h, A.ptr(src), A.ptr(dst), int(n_edges), A.ptr(par),
                                           0 if par is None else par.size), self.ctx.h)
 
+    def append(self, src, dst):
+        """Edges created since the upload (ids continue the upload order); no re-upload of the graph."""
+        src, dst = A.as_i32(src), A.as_i32(dst)
+        A.check(self.L.rrtqx_edges_append(self.h, A.ptr(src), A.ptr(dst), len(src)), self.ctx.h)
+
+    def set_parents(self, node_ids, parent_ids):
+        """makeParentOf for a batch of nodes: parent_ids[i] (or -1) becomes the parent of node_ids[i]."""
+        node_ids, parent_ids = A.as_i32(node_ids), A.as_i32(parent_ids)
+        A.check(self.L.rrtqx_edges_set_parents(self.h, A.ptr(node_ids), A.ptr(parent_ids), len(node_ids)), self.ctx.h)
+
     def add_sweep(self, spheres: SphereSet, ob_ids, robot_radius, delta, flags=0, result: SweepResult | None = None):
         ob_ids = A.as_i32(ob_ids)
         if result is None:

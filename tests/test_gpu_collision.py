@@ -268,3 +268,51 @@ def test_edge_check_grid_path_pathological_obstacles(ctx, building2):
         assert np.array_equal(got, want), variant
         if variant in ("nan_centre", "inf_radius"):
             assert got.all()
+
+
+def test_resident_edge_set_grows_with_the_planner(ctx):
+    """Neighbour-graph residency (rrtqx_edges_append / rrtqx_edges_set_parents): a graph grown in stages --
+    new nodes inserted into the tree, their edges appended, parents re-pointed -- gives the same sweep results
+    as one upload of the final graph (which the test above pins to the oracle)."""
+    pts, _, _ = W.c2_workload(12000, 1)
+    t_full, src, dst, parent = _neighbour_graph(ctx, pts, 2.2)
+    centers, radii = W.c3_obstacles(10)
+    S = SphereSet(ctx, centers, radii)
+    ob_ids = np.arange(len(radii), dtype=np.int32)
+    E_full = EdgeSet(t_full)
+    E_full.upload(src, dst, parent)
+    want_e, want_n = E_full.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA).fetch()
+
+    # staged: nodes [0, n1) with the edges among them, then two more stages
+    t = DeviceTree(ctx, 3)
+    E = EdgeSet(t)
+    stages = [4000, 9000, 12000]
+    eid_map = []                                   # staged edge id -> full edge id
+    prev = 0
+    for k, n_k in enumerate(stages):
+        t.insert_batch(pts[prev:n_k])
+        hi = np.maximum(src, dst)
+        sel = np.nonzero((hi >= prev) & (hi < n_k))[0]   # edges whose later endpoint arrives in this stage
+        par_k = np.where(parent[:n_k] < n_k, parent[:n_k], -1).astype(np.int32)
+        if k == 0:
+            E.upload(src[sel], dst[sel], par_k)
+        else:
+            E.append(src[sel], dst[sel])
+            changed = np.arange(n_k, dtype=np.int32)     # re-point everything (idempotent for unchanged nodes)
+            E.set_parents(changed, par_k)
+        eid_map.append(sel)
+        prev = n_k
+        if k == 1:   # a sweep in the middle of the growth also works (CSR rebuilt lazily)
+            mid = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA)
+            assert mid.sizes()[0] > 0
+    eid_map = np.concatenate(eid_map)
+    assert len(E) == len(src)
+    got_e, got_n = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA).fetch()
+    assert np.array_equal(np.sort(eid_map[got_e]), want_e)
+    # parents that point to a later node were masked to -1 only while that node did not exist; at the end the
+    # parent arrays agree, so the orphan sets agree
+    assert np.array_equal(got_n, want_n)
+    # the statistics kernel (node-centric, uses the CSR + lmax of the rebuilt set) agrees as well
+    st = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS)
+    se, sn = st.fetch()
+    assert np.array_equal(se, got_e) and np.array_equal(sn, got_n)
