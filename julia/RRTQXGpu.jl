@@ -404,4 +404,129 @@ function removeObstacle(G::GpuObstacles, E::GpuEdges, S, KD::GpuKDTree, Q, ob, r
   ob.obstacleUnused = true
 end
 
+# ------------------------------------------------------------------ neighbour-graph residency
+# Edges the planner creates in one iteration (makeNeighborOf / makeInitialOutNeighborOf,
+# DRRT_Q.jl:2589-2593) are appended to the resident set instead of re-uploading the graph; parent
+# edges are re-pointed in place (makeParentOf, DRRT_Q.jl:1841-1856).  `srcIdx`/`dstIdx` are 0-based
+# device node indices (KD.index[node]); edge ids continue the order of E.items.
+function appendEdges!(E::GpuEdges, newEdges::Vector, srcIdx::Vector{Int32}, dstIdx::Vector{Int32})
+  append!(E.items, newEdges)
+  GC.@preserve srcIdx dstIdx check(E.tree.ctx, ccall((:rrtqx_edges_append, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64), E.h, srcIdx, dstIdx, length(srcIdx)))
+end
+
+function setParents!(E::GpuEdges, nodeIdx::Vector{Int32}, parentIdx::Vector{Int32})   # parent -1: rrtParentUsed = false
+  GC.@preserve nodeIdx parentIdx check(E.tree.ctx, ccall((:rrtqx_edges_set_parents, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64), E.h, nodeIdx, parentIdx, length(nodeIdx)))
+end
+
+# ------------------------------------------------------------------ fused per-iteration query
+# One launch for what extend() asks of the geometry per sample (rrtqx.jl:926-950, DRRT_Q.jl:2551-2637):
+# nearest node, explicitNodeCheck of the sample, the shrinking-ball neighbours with their keys, and
+# explicitEdgeCheck of every new edge in both directions.
+function extendQuery(G::GpuObstacles, S, tree::GpuKDTree, point::Array{Float64}, range::Float64; capacity::Int = 8192)
+  nearestIdx = Ref{Int32}(0); nearestDist = Ref{Float64}(0.0)
+  collides = Ref{UInt8}(0); cert = Ref{Float64}(0.0); n = Ref{Int32}(0)
+  idx = Vector{Int32}(undef, capacity); dist = Vector{Float64}(undef, capacity)
+  fwd = Vector{UInt8}(undef, capacity); rev = Vector{UInt8}(undef, capacity)
+  p = vec(point)
+  GC.@preserve p idx dist fwd rev check(tree.ctx, ccall((:rrtqx_extend_query, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, UInt32, Int32, Ref{Int32}, Ref{Float64}, Ref{UInt8},
+       Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}, Ptr{UInt8}),
+      tree.h, G.h, p, range, S.robotRadius, UInt32(4), Int32(capacity), nearestIdx, nearestDist, collides, cert, n,
+      idx, dist, fwd, rev))
+  k = Int(n[])
+  return (tree.nodes[nearestIdx[] + 1], nearestDist[], collides[] != 0, cert[],
+          idx[1:k], dist[1:k], fwd[1:k] .!= 0, rev[1:k] .!= 0)
+end
+
+# ------------------------------------------------------------------ Dubins edges (2-D polygon world)
+mutable struct GpuPolygons
+  ctx::Context
+  h::Ptr{Cvoid}
+  function GpuPolygons(ctx::Context)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:rrtqx_polygons_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, h))
+    o = new(ctx, h[])
+    finalizer(x -> ccall((:rrtqx_polygons_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), o)
+    return o
+  end
+end
+
+# Mirrors S.obstacles (Obstacle kinds 1 and 3, DRRT_data_structures.jl:135-265): bounding circles as the
+# constructor computed them (ob.position, ob.radius), polygon vertices as a CSR.
+function syncPolygons!(G::GpuPolygons, S)
+  kinds = Int32[]; centers = Float64[]; radii = Float64[]; active = UInt8[]; vptr = Int64[0]; verts = Float64[]
+  item = S.obstacles.front
+  for i = 1:S.obstacles.length
+    ob = item.data
+    push!(kinds, Int32(ob.kind)); push!(centers, ob.position[1], ob.position[2]); push!(radii, ob.radius)
+    push!(active, (ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01)
+    if ob.kind == 3
+      for r = 1:size(ob.polygon, 1)
+        push!(verts, ob.polygon[r, 1], ob.polygon[r, 2])
+      end
+    end
+    push!(vptr, length(verts) ÷ 2)
+    item = item.child
+  end
+  GC.@preserve kinds centers radii active vptr verts check(G.ctx, ccall((:rrtqx_polygons_upload, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ptr{Float64}, Int64),
+      G.h, kinds, centers, radii, active, vptr, verts, length(kinds)))
+end
+
+const DUBINS_TYPES = ("rsl", "rsr", "rlr", "lsr", "lsl", "lrl")
+
+# calculateTrajectory(S, edge::DubinsEdge) for a batch of edges (DRRT_DubinsEdge_functions.jl:329-709, space
+# without time): sets dist / distOriginal / Wdist / dubinsType / trajectory on every edge.
+function calculateTrajectoryBatch(ctx::Context, S, edges::Vector)
+  n = length(edges)
+  starts = Matrix{Float64}(undef, 4, n); goals = Matrix{Float64}(undef, 4, n)
+  for (i, e) in enumerate(edges)
+    starts[:, i] = e.startNode.position[1:4]; goals[:, i] = e.endNode.position[1:4]
+  end
+  res = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve starts goals check(ctx, ccall((:rrtqx_dubins_trajectory_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, Ref{Ptr{Cvoid}}), ctx.h, starts, goals, n, S.minTurningRadius, res))
+  ne = Ref{Int64}(0); nr = Ref{Int64}(0)
+  check(ctx, ccall((:rrtqx_dubins_result_sizes, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), res[], ne, nr))
+  dist = Vector{Float64}(undef, n); typ = Vector{Int32}(undef, n); ptr = Vector{Int64}(undef, n + 1)
+  xy = Matrix{Float64}(undef, 2, nr[])
+  GC.@preserve dist typ ptr xy check(ctx, ccall((:rrtqx_dubins_result_fetch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}), res[], dist, typ, ptr, xy))
+  ccall((:rrtqx_dubins_result_destroy, LIB), Int32, (Ptr{Cvoid},), res[])
+  for (i, e) in enumerate(edges)
+    e.dubinsType = typ[i] < 0 ? "xxx" : DUBINS_TYPES[typ[i] + 1]
+    e.Wdist = dist[i]; e.dist = dist[i]; e.distOriginal = dist[i]
+    e.trajectory = permutedims(xy[:, ptr[i]+1:ptr[i+1]])          # rows x 2, as the reference builds it
+  end
+end
+
+# Dubins explicitEdgeCheck(S, edge) OR-ed over the obstacle list for a batch (DRRT_DubinsEdge_functions.jl:750-774).
+function explicitEdgeCheckBatch(G::GpuPolygons, S, edges::Vector)
+  n = length(edges)
+  starts = Matrix{Float64}(undef, 2, n); ends = Matrix{Float64}(undef, 2, n); ptr = Vector{Int64}(undef, n + 1); ptr[1] = 0
+  for (i, e) in enumerate(edges)
+    starts[:, i] = e.startNode.position[1:2]; ends[:, i] = e.endNode.position[1:2]
+    ptr[i + 1] = ptr[i] + size(e.trajectory, 1)
+  end
+  xy = Matrix{Float64}(undef, 2, ptr[end])
+  for (i, e) in enumerate(edges)
+    xy[:, ptr[i]+1:ptr[i+1]] = permutedims(e.trajectory[:, 1:2])
+  end
+  out = Vector{UInt8}(undef, n)
+  GC.@preserve starts ends ptr xy out check(G.ctx, ccall((:rrtqx_dubins_edge_check_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Int64, Float64, Float64, UInt32, Ptr{UInt8}),
+      G.h, starts, ends, ptr, xy, n, S.robotRadius, S.minTurningRadius, UInt32(0), out))
+  return S.inWarmupTime ? falses(n) : out .!= 0
+end
+
+# saturate(newPoint, closestPoint, delta), DubinsEdge version (DRRT_DubinsEdge_functions.jl:70-95): in place.
+function saturateDubins!(ctx::Context, newPoint::Array{Float64}, closestPoint::Array{Float64}, delta::Float64)
+  p = vec(newPoint); c = vec(closestPoint)
+  GC.@preserve p c check(ctx, ccall((:rrtqx_dubins_saturate_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64), ctx.h, p, c, 1, delta))
+  newPoint[:] = p
+end
+
 end # module
