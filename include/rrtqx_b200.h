@@ -116,6 +116,11 @@ RRTQX_API rrtqx_status rrtqx_tree_kd_fields(rrtqx_tree *tree, int64_t first,
                                             int32_t *child_l, int32_t *child_r,
                                             int32_t *split);
 /* Copies positions of nodes [first, first+count) back (row-major). */
+/* order_out[k] = node visited k-th by the reference's recursive kd traversal (node, kdChildL subtree,
+ * kdChildR subtree): the row order of saveRRTNodes / saveRRTTree / saveRRTGraph (DRRT_Q.jl:252-337).
+ * order_out: host array of tree-size entries. */
+RRTQX_API rrtqx_status rrtqx_tree_preorder(rrtqx_tree *tree,
+                                           int32_t *order_out);
 RRTQX_API rrtqx_status rrtqx_tree_positions(rrtqx_tree *tree, int64_t first,
                                             int64_t count, double *out);
 /* Tuning knob of the device index: mean points per grid cell the next

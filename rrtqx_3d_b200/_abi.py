@@ -42,6 +42,7 @@ SIGNATURES = {
     "rrtqx_tree_size": (i32, [vp, C.POINTER(i64)]),
     "rrtqx_tree_kd_fields": (i32, [vp, i64, i64, vp, vp, vp, vp]),
     "rrtqx_tree_positions": (i32, [vp, i64, i64, vp]),
+    "rrtqx_tree_preorder": (i32, [vp, vp]),
     "rrtqx_tree_set_cell_occupancy": (i32, [vp, f64]),
     "rrtqx_tree_reindex": (i32, [vp]),
     "rrtqx_range_query_batch": (i32, [vp, vp, i64, f64, vp, u32, C.POINTER(vp), C.POINTER(i64)]),

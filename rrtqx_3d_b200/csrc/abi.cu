@@ -222,6 +222,37 @@ rrtqx_status rrtqx_tree_kd_fields(rrtqx_tree *tree, int64_t first, int64_t count
   });
 }
 
+// Visit order of the reference's recursive kd traversals (saveRRTSubNodes / saveRRTSubTree / saveRRTSubGraph,
+// DRRT_Q.jl:252-337: node, then kdChildL subtree, then kdChildR subtree).  One bulk copy of the child links, then
+// an explicit-stack walk on the host: export for the visualisation dumps, not a hot path.
+rrtqx_status rrtqx_tree_preorder(rrtqx_tree *tree, int32_t *order_out) {
+  if (!tree) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    const int64_t n = tree->n;
+    RQ_REQUIRE(order_out != nullptr || n == 0, "order_out is NULL");
+    RQ_REQUIRE(!is_device_ptr(order_out), "order_out must be a host array");
+    if (n == 0) return;
+    std::vector<unsigned> child(2 * (size_t)n);
+    RQ_CUDA(cudaMemcpyAsync(child.data(), tree->child.p, sizeof(unsigned) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> stack;
+    stack.push_back(0);
+    int64_t k = 0;
+    while (!stack.empty()) {
+      const int32_t v = stack.back();
+      stack.pop_back();
+      RQ_REQUIRE(k < n, "kd links are inconsistent");
+      order_out[k++] = v;
+      const unsigned l = child[2 * (size_t)v], r = child[2 * (size_t)v + 1];
+      if (r != KD_EMPTY) stack.push_back((int32_t)r);  // right is visited after the whole left subtree
+      if (l != KD_EMPTY) stack.push_back((int32_t)l);
+    }
+    RQ_REQUIRE(k == n, "kd links do not reach every node");
+  });
+}
+
 rrtqx_status rrtqx_tree_positions(rrtqx_tree *tree, int64_t first, int64_t count, double *out) {
   if (!tree) return RRTQX_ERR_INVALID;
   rrtqx_ctx *ctx = tree->ctx;

@@ -162,6 +162,12 @@ class DeviceTree:
         A.check(self.L.rrtqx_tree_positions(self.h, first, count, A.ptr(out)), self.ctx.h)
         return out
 
+    def preorder(self):
+        """Node indices in the visit order of the reference's recursive kd traversals (dump row order)."""
+        out = np.empty(len(self), dtype=np.int32)
+        A.check(self.L.rrtqx_tree_preorder(self.h, A.ptr(out)), self.ctx.h)
+        return out
+
     def set_cell_occupancy(self, ppc: float):
         A.check(self.L.rrtqx_tree_set_cell_occupancy(self.h, float(ppc)), self.ctx.h)
 

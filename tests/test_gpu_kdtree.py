@@ -194,3 +194,31 @@ def test_empty_tree_is_an_error(ctx):
     assert e.value.status == ERR_EMPTY_TREE
     with pytest.raises(RRTQXError):
         t.nearest(np.zeros((1, 3)))
+
+
+def test_preorder_is_the_reference_traversal_order(ctx):
+    """rrtqx_tree_preorder: node, kdChildL subtree, kdChildR subtree (saveRRTSubNodes, DRRT_Q.jl:316-327),
+    checked against a recursive walk over the ORACLE's kd links."""
+    import sys
+    pts = _points(9, 30000, 3)
+    orc = oracle.KDTree(3)
+    orc.insert_batch(pts)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts[:20000])
+    for p in pts[20000:20050]:
+        t.insert(p)                       # single inserts take the one-thread walk
+    t.insert_batch(pts[20050:])
+    parent, left, right, split = orc.fields()
+    want = []
+    sys.setrecursionlimit(10000)
+
+    def walk(v):
+        want.append(v)
+        if left[v] >= 0:
+            walk(left[v])
+        if right[v] >= 0:
+            walk(right[v])
+    walk(0)
+    got = t.preorder()
+    assert np.array_equal(got, np.asarray(want, dtype=np.int32))
+    assert sorted(got.tolist()) == list(range(len(pts)))
