@@ -152,8 +152,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "kd_range_queries_per_s", "value": value, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 batched neighbour sweep (CPU arm: bounded sample per step)",
-                       "nodes": args.nodes, "queries_per_step": sample, "radius": r},
+            "config": {"workload": "C2 batched neighbour sweep: 1M-node uniform 3-D tree, kdFindWithinRange at the RRTx "
+                                   "shrinking-ball radius, idx + distance keys",
+                       "nodes": args.nodes, "queries_per_gpu": args.queries, "radius": r,
+                       "cpu_arm": f"each step is a bounded sample of {sample} queries of the workload (all host threads)"},
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
                              "sample": f"{sample} C2 queries per step (oracle port of kdFindWithinRange, pthreads)"},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
