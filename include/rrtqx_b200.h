@@ -79,6 +79,10 @@ RRTQX_API rrtqx_status rrtqx_ctx_kernel_launches(const rrtqx_ctx *ctx,
 /* CUDA-event timing of the context's most recent named phase, in ms; phase is
  * one of "range_query", "nearest", "edge_check", "node_check", "add_sweep",
  * "remove_sweep", "tree_build".  Measured on the context's stream. */
+/* measured FP64 FMA throughput of the device (TFLOP/s, 2 flop per FMA): the roofline denominator of the
+ * FP64-bound collision kernels, taken in the same run as the numbers it normalises */
+RRTQX_API rrtqx_status rrtqx_ctx_measure_fp64_peak(rrtqx_ctx *ctx,
+                                                   double *tflops);
 RRTQX_API rrtqx_status rrtqx_ctx_last_phase_ms(rrtqx_ctx *ctx,
                                                const char *phase, float *ms);
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "rrtqx_ctx_sync": (i32, [vp]),
     "rrtqx_ctx_kernel_launches": (i32, [vp, C.POINTER(i64)]),
     "rrtqx_ctx_last_phase_ms": (i32, [vp, C.c_char_p, C.POINTER(C.c_float)]),
+    "rrtqx_ctx_measure_fp64_peak": (i32, [vp, C.POINTER(f64)]),
     "rrtqx_tree_create": (i32, [vp, i32, i32, vp, vp, C.POINTER(vp)]),
     "rrtqx_tree_destroy": (i32, [vp]),
     "rrtqx_tree_insert_batch": (i32, [vp, vp, i64, C.POINTER(i32)]),

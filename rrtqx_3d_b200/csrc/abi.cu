@@ -112,6 +112,50 @@ rrtqx_status rrtqx_ctx_last_phase_ms(rrtqx_ctx *ctx, const char *phase, float *m
   });
 }
 
+// ---------------------------------------------------------- measured FP64 peak
+// Roofline denominator of the FP64-bound kernels (collision sweeps): 8 independent DFMA chains per thread,
+// full occupancy, timed with events on the context's stream.  Not in MEASURED_PEAKS.json, so it is measured
+// in the bench run itself ("measure it").
+namespace rrtqx {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+    x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+}  // namespace rrtqx
+
+rrtqx_status rrtqx_ctx_measure_fp64_peak(rrtqx_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    cudaStream_t st = ctx->stream;
+    ctx->stage_f64.ensure(16, st);
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t a, b;
+    RQ_CUDA(cudaEventCreate(&a));
+    RQ_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      RQ_CUDA(cudaEventRecord(a, st));
+      fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->stage_f64.p, iters, 0.999999, 1e-9);
+      post_launch(ctx);
+      RQ_CUDA(cudaEventRecord(b, st));
+      RQ_CUDA(cudaEventSynchronize(b));
+      float ms = 0.f;
+      RQ_CUDA(cudaEventElapsedTime(&ms, a, b));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const double flop = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flop / ((double)best * 1e-3) / 1e12;
+  });
+}
+
 // ------------------------------------------------------------------- tree
 rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d, int32_t num_wraps, const int32_t *wraps,
                                const double *wrap_points, rrtqx_tree **out) {

@@ -42,6 +42,12 @@ class Context:
         A.check(self.L.rrtqx_ctx_kernel_launches(self.h, C.byref(n)), self.h)
         return int(n.value)
 
+    def measure_fp64_peak(self) -> float:
+        """Measured FP64 FMA throughput in TFLOP/s (roofline denominator of the FP64-bound collision kernels)."""
+        v = A.f64(0.0)
+        A.check(self.L.rrtqx_ctx_measure_fp64_peak(self.h, C.byref(v)), self.h)
+        return float(v.value)
+
     def last_phase_ms(self, phase: str) -> float:
         ms = C.c_float(0.0)
         A.check(self.L.rrtqx_ctx_last_phase_ms(self.h, phase.encode(), C.byref(ms)), self.h)
