@@ -336,7 +336,8 @@ static void range_query_impl(rrtqx_tree *t, const double *queries, int64_t nq, d
   PhaseScope ph(ctx, "range_query");
   res->counts.ensure((size_t)nq + 1, st);
   res->offsets.ensure((size_t)nq + 1, st);
-  if (t->wrap.num_wraps == 0 && !getenv("RRTQX_RANGE_TWO_PASS")) {
+  // the single-pass kernels pack (slot << 4 | count) into 32-bit octet-table entries: slots below 2^27
+  if (t->wrap.num_wraps == 0 && !getenv("RRTQX_RANGE_TWO_PASS") && t->n_sorted < ((int64_t)1 << 27)) {
     range_query_fused<D>(t, dq, dr, nq, r, flags, res);
     return;
   }
