@@ -416,12 +416,16 @@ def main():
     res = RangeResult(ctx)
     gathered = torch.empty(world * args.queries, dtype=torch.int32, device="cuda") if world > 1 else None
 
+    counts_view = {}
+
     def step():
         _, total = tree.range_query(dq, r, want_dist=True, result=res, n_queries=args.queries)
         if world > 1:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink)
             cptr = res.device_pointers()[0]
-            counts_t = tensor_from_ptr(torch, cptr, args.queries, torch.int32)
-            dist.all_gather_into_tensor(gathered, counts_t)
+            if cptr not in counts_view:      # the library's buffers are grow-only: the view is built once
+                counts_view.clear()
+                counts_view[cptr] = tensor_from_ptr(torch, cptr, args.queries, torch.int32)
+            dist.all_gather_into_tensor(gathered, counts_view[cptr])
         return total
 
     def tensor_from_ptr(torch_mod, p, n, dtype):
