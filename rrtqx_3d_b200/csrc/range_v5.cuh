@@ -237,6 +237,9 @@ struct V5Params {
   float invx, invy, invz, celly, cellz;
 };
 
+// floor + clamp to [0, n-1] through the integer converter (F2I.FLOOR saturates, NaN -> 0): 3 instructions
+__device__ __forceinline__ int clampi_fast(float v, int n) { return min(max(__float2int_rd(v), 0), n - 1); }
+
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -339,12 +342,12 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
           int cy0 = 0x7fffffff, cy1 = -1, cz0 = 0, cz1 = 0;
           if (D >= 3) { cz0 = 0x7fffffff; cz1 = -1; }
           if (live0) {
-            cy0 = clampi(ff0[1] - ry0, g.ny); cy1 = clampi(ff0[1] + ry0, g.ny);
-            if (D >= 3) { cz0 = clampi(ff0[2] - rz0, g.nz); cz1 = clampi(ff0[2] + rz0, g.nz); }
+            cy0 = clampi_fast(ff0[1] - ry0, g.ny); cy1 = clampi_fast(ff0[1] + ry0, g.ny);
+            if (D >= 3) { cz0 = clampi_fast(ff0[2] - rz0, g.nz); cz1 = clampi_fast(ff0[2] + rz0, g.nz); }
           }
           if (live1) {
-            cy0 = min(cy0, clampi(ff1[1] - ry1, g.ny)); cy1 = max(cy1, clampi(ff1[1] + ry1, g.ny));
-            if (D >= 3) { cz0 = min(cz0, clampi(ff1[2] - rz1, g.nz)); cz1 = max(cz1, clampi(ff1[2] + rz1, g.nz)); }
+            cy0 = min(cy0, clampi_fast(ff1[1] - ry1, g.ny)); cy1 = max(cy1, clampi_fast(ff1[1] + ry1, g.ny));
+            if (D >= 3) { cz0 = min(cz0, clampi_fast(ff1[2] - rz1, g.nz)); cz1 = max(cz1, clampi_fast(ff1[2] + rz1, g.nz)); }
           }
           const int wy = cy1 - cy0 + 1;
           const int sh = 32 - __clz(wy - 1);  // wy = 1 -> 0
@@ -371,8 +374,8 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
                 if (rem >= 0.0f) {
                   // sqrt.approx: 2 ulp, inside the 1e-5 inflation; an infinite r2f gives the whole row
                   const float xc = sqrt_approx(rem) * (1.0f + 1e-5f) * invx + 1e-3f;
-                  ca = min(ca, clampi(ff[0] - xc, g.nx));
-                  cb = max(cb, clampi(ff[0] + xc, g.nx));
+                  ca = min(ca, clampi_fast(ff[0] - xc, g.nx));
+                  cb = max(cb, clampi_fast(ff[0] + xc, g.nx));
                 }
               };
               span(ff0, R0.r2f);
@@ -432,15 +435,13 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
         // group i, so a warp always has V5_U 128-bit loads in flight while it computes.
         int jj[V5_U];
         float4 c[V5_U];
-        unsigned vmask = 0;  // bit u: this lane's slot of trip u is valid
+        const int dummy = g.n_sorted + 7;  // padding record of +inf coordinates: s' = +inf (miss, outside the band)
         auto load_group = [&](unsigned tb) {
           const unsigned taddr = tb + goff;
-          vmask = 0;
 #pragma unroll
           for (int u = 0; u < V5_U; ++u) {
             const int ent = lds32(taddr + 16u * u);
-            if (sub < (unsigned)(ent & 15)) vmask |= 1u << u;
-            jj[u] = (ent >> 4) + (int)sub;  // invalid lanes read inside the 8-record padding
+            jj[u] = sub < (unsigned)(ent & 15) ? (ent >> 4) + (int)sub : dummy;  // lanes past the octet's end
           }
 #pragma unroll
           for (int u = 0; u < V5_U; ++u) {
@@ -455,8 +456,7 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
           float band = INFINITY;  // min |s'| over the group's tests of this lane
 #pragma unroll
           for (int u = 0; u < V5_U; ++u) {
-            const float cx = (vmask >> u) & 1u ? c[u].x : INFINITY;  // invalid lane: s' = +inf (miss, outside the band)
-            unsigned long long s2 = sub2(qx2, pk2(cx, cx));
+            unsigned long long s2 = sub2(qx2, pk2(c[u].x, c[u].x));
             s2 = fma2(s2, s2, nT2);
             unsigned long long d2 = sub2(qy2, pk2(c[u].y, c[u].y));
             s2 = fma2(d2, d2, s2);

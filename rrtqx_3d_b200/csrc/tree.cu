@@ -249,6 +249,10 @@ __global__ void cell_gather_kernel(const double4 *__restrict__ pos, const int32_
                                    float *__restrict__ fmaxabs) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float m = 0.0f;
+  if (j >= n && j < n + 8) {  // the 8 padding slots behind the last record never hit: +inf filter coordinates
+    f4[j] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    d4[j] = make_double4(INFINITY, INFINITY, INFINITY, __longlong_as_double(-1LL));
+  }
   if (j < n) {
     const int node = sperm[j];
     double4 p = pos[node];
@@ -365,7 +369,7 @@ void tree_reindex(rrtqx_tree *t) {
   RQ_CUDA(cudaMemsetAsync(t->cell_cursor.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   cell_scatter_kernel<<<div_up(n, TB), TB, 0, st>>>(t->cell_id.p, n, t->cell_start.p, t->cell_cursor.p, t->sperm.p);
   cell_sort_kernel<<<div_up(ncell, TB), TB, 0, st>>>(t->cell_start.p, ncell, t->sperm.p);
-  cell_gather_kernel<<<div_up(n, TB), TB, 0, st>>>(t->pos.p, t->sperm.p, n, t->d, t->lo[0], t->lo[1], t->lo[2], t->sx.p, t->sy.p,
+  cell_gather_kernel<<<div_up(n + 8, TB), TB, 0, st>>>(t->pos.p, t->sperm.p, n, t->d, t->lo[0], t->lo[1], t->lo[2], t->sx.p, t->sy.p,
                                                    t->sz.p, t->sw.p, t->f4.p, t->d4.p, t->fmaxabs.p);
   post_launch(ctx, 3);
 }
