@@ -503,6 +503,24 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps}
 
+    # ------------------------------------------------------- extra: batched kdFindNearest on the same workload
+    try:
+        nn_idx = torch.empty(args.queries, dtype=torch.int32, device="cuda")
+        nn_dist = torch.empty(args.queries, dtype=torch.float64, device="cuda")
+        nts = []
+        for it in range(3 + max(3, min(args.steps, 10))):
+            flush.zero_()
+            tree.nearest(dq.data_ptr(), n_queries=args.queries, idx_out=nn_idx.data_ptr(), dist_out=nn_dist.data_ptr())
+            if it >= 3:
+                nts.append(ctx.last_phase_ms("nearest"))
+        nms = float(np.mean(nts))
+        nbytes = args.nodes * 24 + args.queries * 24 + args.queries * 12
+        line["nearest"] = {"workload": "kdFindNearest for the same 1M queries (query sort + thread-per-query kernel)",
+                           "ms": nms, "queries_per_s": args.queries / (nms / 1e3), "algorithmic_bytes": nbytes,
+                           "hbm_frac": nbytes / (nms / 1e3) / 1e9 / peak_gbs}
+    except Exception as exc:
+        line["nearest"] = {"error": repr(exc)}
+
     # ------------------------------------------------------- e2e (host buffers)
     if not args.no_e2e:
         hq = torch.from_numpy(qs).pin_memory()

@@ -514,6 +514,83 @@ nearest_kernel(GridView g, WrapInfo wrap, const double *__restrict__ queries, co
   }
 }
 
+
+// Thread-per-query nearest for large batches over a fully indexed tree (no unsorted tail, no wrap-around):
+// a query needs its home cell and the few neighbouring cells closer than the best distance so far -- a dozen
+// points -- so a warp per query idles 30 lanes.  The home cell (or the 3^3 block around an empty one) seeds
+// the best radicand; the box of cells within that distance is then scanned, each cell skipped when a
+// conservative lower bound of its distance exceeds the best radicand.  Queries whose box is wider than
+// 2*NN_RHO_MAX+1 cells (far outside the grid, empty regions) are handed to the warp-per-query kernel.
+// Result semantics identical to nearest_kernel: minimum radicand, ties to the smallest node index.
+constexpr int NN_RHO_MAX = 3;
+
+template <int D>
+__global__ void __launch_bounds__(128)
+nearest_tpq_kernel(GridView g, const double *__restrict__ queries, const int32_t *__restrict__ qorder, int64_t nq,
+                   int32_t *__restrict__ out_idx, double *__restrict__ out_dist, int32_t *__restrict__ unresolved,
+                   int32_t *__restrict__ n_unresolved) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int qid = qorder[i];
+  double q[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) q[k] = queries[(int64_t)qid * D + k];
+  double bs = INFINITY;
+  int bn = 0x7fffffff;
+  const int cx = cell_of(q[0], g.lo[0], g.inv[0], g.nx);
+  const int cy = cell_of(q[1], g.lo[1], g.inv[1], g.ny);
+  const int cz = D >= 3 ? cell_of(q[2], g.lo[2], g.inv[2], g.nz) : 0;
+  const double slack = 1e-9 * fmax(g.cell[0], fmax(g.cell[1], g.cell[2])) +
+                       1e-12 * (fabs(q[0]) + fabs(q[1]) + (D >= 3 ? fabs(q[2]) : 0.0));
+  // conservative lower bound of |p_c - q_c| for a point stored in cell k of axis c
+  auto gap = [&](int c, int k) {
+    const double lo_k = g.lo[c] + k * g.cell[c], hi_k = lo_k + g.cell[c];
+    return fmax(0.0, fmax(lo_k - q[c], q[c] - hi_k) - slack);
+  };
+  auto scan_cell = [&](int x, int y, int z) {
+    const double gx = gap(0, x), gy = gap(1, y), gz = D >= 3 ? gap(2, z) : 0.0;
+    if ((gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9) > bs) return;  // cannot beat (or tie) the best
+    const int c = (z * g.ny + y) * g.nx + x;
+    const int a = g.cell_start[c], b = g.cell_start[c + 1];
+    for (int j = a; j < b; ++j) {
+      const double4 p = g.d4[j];
+      const int node = D <= 3 ? (int)__double_as_longlong(p.w) : g.sperm[j];
+      const double s = sqdist<D>(q, p.x, p.y, p.z, p.w);
+      if (s < bs || (s == bs && node < bn)) { bs = s; bn = node; }
+    }
+  };
+  // 1. seed: the home cell, else (empty home cell) the 3 x 3 x 3 block around it
+  bool done = false;
+  scan_cell(cx, cy, cz);
+  if (bn == 0x7fffffff) {
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y)
+        for (int x = max(cx - 1, 0); x <= min(cx + 1, g.nx - 1); ++x)
+          if (x != cx || y != cy || z != cz) scan_cell(x, y, z);
+  }
+  if (bn != 0x7fffffff) {
+    // 2. every point that can beat or tie the seed lies within d = sqrt(bs) of q, hence (cell_of is monotone)
+    // in the cells of the box [cell_of(q - d), cell_of(q + d)]; scan that box when it is small
+    const double d = __dsqrt_rn(bs) * (1.0 + 1e-9) + slack;
+    const int xa = cell_of(q[0] - d, g.lo[0], g.inv[0], g.nx), xb = cell_of(q[0] + d, g.lo[0], g.inv[0], g.nx);
+    const int ya = cell_of(q[1] - d, g.lo[1], g.inv[1], g.ny), yb = cell_of(q[1] + d, g.lo[1], g.inv[1], g.ny);
+    const int za = D >= 3 ? cell_of(q[2] - d, g.lo[2], g.inv[2], g.nz) : 0;
+    const int zb = D >= 3 ? cell_of(q[2] + d, g.lo[2], g.inv[2], g.nz) : 0;
+    if (xb - xa <= 2 * NN_RHO_MAX && yb - ya <= 2 * NN_RHO_MAX && zb - za <= 2 * NN_RHO_MAX && isfinite(d)) {
+      for (int z = za; z <= zb; ++z)
+        for (int y = ya; y <= yb; ++y)
+          for (int x = xa; x <= xb; ++x) scan_cell(x, y, z);   // cells already seen are re-pruned or re-scanned (idempotent)
+      done = true;
+    }
+  }
+  if (done && bn != 0x7fffffff) {
+    out_idx[qid] = bn;
+    if (out_dist) out_dist[qid] = __dsqrt_rn(bs);
+  } else {
+    unresolved[atomicAdd(n_unresolved, 1)] = qid;  // finished by the warp-per-query kernel
+  }
+}
+
 struct NearestScratch {
   rrtqx_range_result sortbuf;  // reuses the query sort buffers
   DevBuf<int32_t> idx;
@@ -533,17 +610,36 @@ static void nearest_impl(rrtqx_tree *t, rrtqx_range_result *sortbuf, const doubl
   if (!idx_dev) { idx_stage.ensure((size_t)nq, st); didx = idx_stage.p; }
   if (dist_out && !dist_dev) { dist_stage.ensure((size_t)nq, st); ddist = dist_stage.p; }
   {
+    // large batches over a tree without wrap-around: index the tail first, then one thread per query
+    const bool tpq = t->wrap.num_wraps == 0 && nq >= 4096 && !getenv("RRTQX_NEAREST_WARP");
+    if (tpq && t->n_sorted < t->n) tree_reindex(t);
     PhaseScope ph(ctx, "nearest");
     sort_queries<D>(t, sortbuf, dq, nq);
     GridView g = t->view();
     const int TB = 256;
-    int blocks = (int)std::min<int64_t>((nq * 32 + TB - 1) / TB, (int64_t)ctx->sm_count * 8);
-    if (blocks < 1) blocks = 1;
-    if (t->wrap.num_wraps > 0)
-      nearest_kernel<D, true><<<blocks, TB, 0, st>>>(g, t->wrap, dq, sortbuf->qorder.p, nq, didx, ddist);
-    else
-      nearest_kernel<D, false><<<blocks, TB, 0, st>>>(g, t->wrap, dq, sortbuf->qorder.p, nq, didx, ddist);
-    post_launch(ctx);
+    auto warp_kernel = [&](const int32_t *order, int64_t n) {
+      int blocks = (int)std::min<int64_t>((n * 32 + TB - 1) / TB, (int64_t)ctx->sm_count * 8);
+      if (blocks < 1) blocks = 1;
+      if (t->wrap.num_wraps > 0)
+        nearest_kernel<D, true><<<blocks, TB, 0, st>>>(g, t->wrap, dq, order, n, didx, ddist);
+      else
+        nearest_kernel<D, false><<<blocks, TB, 0, st>>>(g, t->wrap, dq, order, n, didx, ddist);
+      post_launch(ctx);
+    };
+    if (tpq && t->n_sorted > 0) {
+      sortbuf->qkey.ensure((size_t)nq + 1, st);          // free after the sort: list of unresolved queries
+      t->flagbuf.ensure(8, st);
+      RQ_CUDA(cudaMemsetAsync(t->flagbuf.p, 0, sizeof(int32_t), st));
+      nearest_tpq_kernel<D><<<div_up(nq, 128), 128, 0, st>>>(g, dq, sortbuf->qorder.p, nq, didx, ddist, sortbuf->qkey.p,
+                                                            t->flagbuf.p);
+      post_launch(ctx);
+      int32_t n_unres = 0;
+      RQ_CUDA(cudaMemcpyAsync(&n_unres, t->flagbuf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RQ_CUDA(cudaStreamSynchronize(st));
+      if (n_unres > 0) warp_kernel(sortbuf->qkey.p, n_unres);
+    } else {
+      warp_kernel(sortbuf->qorder.p, nq);
+    }
   }
   if (!idx_dev) from_device(ctx, idx_out, didx, (size_t)nq);
   if (dist_out && !dist_dev) from_device(ctx, dist_out, ddist, (size_t)nq);

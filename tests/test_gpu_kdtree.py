@@ -222,3 +222,27 @@ def test_preorder_is_the_reference_traversal_order(ctx):
     got = t.preorder()
     assert np.array_equal(got, np.asarray(want, dtype=np.int32))
     assert sorted(got.tolist()) == list(range(len(pts)))
+
+
+def test_nearest_large_batch_thread_per_query_and_fallback(ctx):
+    """Batches >= 4096 take the thread-per-query kernel; queries far outside the grid or in empty regions are
+    finished by the warp-per-query kernel; a pending unsorted tail is indexed first.  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(13)
+    clustered = np.concatenate([rng.normal(size=(20000, 3)) * 0.5 + c for c in ([-15, -15, -15], [10, 12, -3], [0, 0, 18])])
+    pts = np.ascontiguousarray(np.concatenate([clustered, _points(5, 5000, 3)]))
+    orc = oracle.KDTree(3)
+    orc.insert_batch(pts)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts[:60000])
+    t.range_query(pts[:10], 1.0)                      # builds the index over the first 60000 nodes
+    for p in pts[60000:60200]:
+        t.insert(p)                                   # unsorted tail
+    t.insert_batch(pts[60200:])
+    qs = _points(6, 6000, 3)                          # mostly empty space between the clusters
+    qs[:200] = qs[:200] * 50.0                        # far outside the bounding box
+    qs[200:400] = pts[:200]                           # exactly on nodes (distance 0)
+    qs[400:600] = clustered[:200] + 1e-9
+    gi, gd = t.nearest(qs)
+    oi, od = orc.nearest_batch(qs, nthreads=8)
+    assert np.array_equal(gd.view(np.uint64), od.view(np.uint64))
+    assert np.array_equal(gi, oi)
