@@ -170,9 +170,10 @@ def test_range_sees_unsorted_tail_after_inserts(ctx):
     assert np.array_equal(gi, oi)
 
 
-@pytest.mark.parametrize("d,wrap", [(3, False), (2, False), (4, True)])
-def test_nearest_bitexact(ctx, d, wrap):
-    pts, qs = _points(3, 20000, d), _points(4, 3000, d)
+@pytest.mark.parametrize("d,wrap,nq", [(3, False, 3000), (2, False, 3000), (4, True, 3000),
+                                       (2, False, 6000), (4, False, 6000), (4, True, 6000)])   # >= 4096: thread per query
+def test_nearest_bitexact(ctx, d, wrap, nq):
+    pts, qs = _points(3, 20000, d), _points(4, nq, d)
     kw = dict(wraps=[3], wrap_points=[TWO_PI]) if wrap else {}
     orc = oracle.KDTree(d, **kw)
     orc.insert_batch(pts)
