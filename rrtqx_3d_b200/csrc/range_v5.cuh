@@ -236,6 +236,7 @@ __host__ __device__ __forceinline__ V5Radius v5_radius(double r, double T, bool 
 struct V5Params {
   V5Radius RU;
   float invx, invy, invz, celly, cellz;
+  unsigned unit;  // pairs per dynamically scheduled unit of work
 };
 
 // floor + clamp to [0, n-1] through the integer converter (F2I.FLOOR saturates, NaN -> 0): 3 instructions
@@ -289,11 +290,11 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
       unsigned tk = 0;
       if (lane == 0) tk = atomicAdd(&s_ticket, 1u);
       tk = __shfl_sync(FULL, tk, 0);
-      const unsigned unit = tk / V5_UNIT, off = tk % V5_UNIT, slot = unit % V5_RING;
+      const unsigned unit = tk / P.unit, off = tk - unit * P.unit, slot = unit % V5_RING;
       long long base = 0;
       if (lane == 0) {
         if (off == 0) {
-          base = (long long)atomicAdd(&cursor[1], (unsigned long long)V5_UNIT);
+          base = (long long)atomicAdd(&cursor[1], (unsigned long long)P.unit);
           s_base[slot] = base;
           __threadfence_block();
           atomicExch(&s_pub[slot], unit + 1u);
@@ -647,7 +648,9 @@ static void launch_v5(rrtqx_ctx *ctx, const GridView &g, const double *dq, const
   P.RU = v5_radius(r, T, true);
   P.invx = (float)g.inv[0]; P.invy = (float)g.inv[1]; P.invz = (float)g.inv[2];
   P.celly = (float)g.cell[1]; P.cellz = (float)g.cell[2];
-  const int64_t n_units = ((nq + 1) / 2 + V5_UNIT - 1) / V5_UNIT;
+  static const unsigned unit_env = [] { const char *e = getenv("RRTQX_V5_UNIT"); int v = e ? atoi(e) : 0; return (unsigned)(v > 0 ? v : 0); }();
+  P.unit = unit_env ? unit_env : (unsigned)V5_UNIT;
+  const int64_t n_units = ((nq + 1) / 2 + P.unit - 1) / P.unit;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)ctx->sm_count));
   if (dr)
     range_v5_kernel<D, NW, CAP, TAB, false><<<blocks, NW * 32, smem, ctx->stream>>>(g, P, dq, dqs, qorder, nq, r, T, dr, dT, counts,
