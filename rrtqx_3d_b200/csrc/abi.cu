@@ -209,7 +209,14 @@ rrtqx_status rrtqx_tree_insert_batch(rrtqx_tree *tree, const double *positions, 
 }
 
 rrtqx_status rrtqx_tree_insert(rrtqx_tree *tree, const double *position, int32_t *index_out) {
-  return rrtqx_tree_insert_batch(tree, position, 1, index_out);
+  if (!tree) return RRTQX_ERR_INVALID;
+  if (position && is_device_ptr(position)) return rrtqx_tree_insert_batch(tree, position, 1, index_out);
+  return guarded(tree->ctx, [&] {
+    bind_device(tree->ctx);
+    RQ_REQUIRE(position != nullptr, "position is NULL");
+    if (index_out) *index_out = (int32_t)tree->n;
+    tree_insert_point(tree, position);  // stream-ordered: later calls on this context see the node
+  });
 }
 
 rrtqx_status rrtqx_tree_size(const rrtqx_tree *tree, int64_t *n) {

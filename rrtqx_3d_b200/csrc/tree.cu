@@ -121,6 +121,56 @@ __global__ void kd_insert_one_kernel(const double4 *__restrict__ pos, unsigned *
   }
 }
 
+// The planner's per-iteration insert in ONE launch: the position travels as a kernel argument (no staging
+// copy, nothing to wait for), the thread initialises the node's records and walks down to its slot.
+__global__ void kd_insert_point_kernel(double4 p, double4 *__restrict__ pos, unsigned *__restrict__ child,
+                                       int32_t *__restrict__ parent, int8_t *__restrict__ split, int32_t *__restrict__ cur,
+                                       int64_t i, int d) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  pos[i] = p;
+  child[2 * i] = KD_EMPTY;
+  child[2 * i + 1] = KD_EMPTY;
+  parent[i] = -1;
+  split[i] = 0;
+  cur[i] = -1;
+  if (i == 0) return;  // root: split 0 (kdTree_general.jl:127-132)
+  int32_t q = 0;
+  for (;;) {
+    const int s = split[q];
+    const int side = coord(p, s) < coord(pos[q], s) ? 0 : 1;
+    const unsigned c = child[2 * (int64_t)q + side];
+    if (c == KD_EMPTY) {
+      child[2 * (int64_t)q + side] = (unsigned)i;
+      parent[i] = q;
+      split[i] = (int8_t)((s == d - 1) ? 0 : s + 1);
+      return;
+    }
+    q = (int32_t)c;
+  }
+}
+
+// Single insert of a HOST position (rrtqx_tree_insert): asynchronous, one launch.
+void tree_insert_point(rrtqx_tree *t, const double *position) {
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(t->n + 1 < (int64_t)0x7fffffff, "tree too large for int32 node indices");
+  const int64_t first = t->n;
+  const size_t need = (size_t)(first + 1);
+  t->pos.ensure(need, st, (size_t)first);
+  t->child.ensure(2 * need, st, 2 * (size_t)first);
+  t->parent.ensure(need, st, (size_t)first);
+  t->split.ensure(need, st, (size_t)first);
+  t->cur.ensure(need, st, (size_t)first);
+  double4 p;
+  p.x = position[0];
+  p.y = position[1];
+  p.z = t->d >= 3 ? position[2] : 0.0;
+  p.w = t->d >= 4 ? position[3] : 0.0;
+  kd_insert_point_kernel<<<1, 32, 0, st>>>(p, t->pos.p, t->child.p, t->parent.p, t->split.p, t->cur.p, first, t->d);
+  post_launch(ctx);
+  t->n = first + 1;
+}
+
 void tree_insert_batch(rrtqx_tree *t, const double *positions, int64_t n_new) {
   if (n_new <= 0) return;
   rrtqx_ctx *ctx = t->ctx;

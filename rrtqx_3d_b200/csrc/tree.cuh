@@ -104,6 +104,7 @@ struct rrtqx_tree {
 
 namespace rrtqx {
 void tree_insert_batch(rrtqx_tree *t, const double *positions, int64_t n);
+void tree_insert_point(rrtqx_tree *t, const double *host_position);  // one node, one launch, asynchronous
 void tree_reindex(rrtqx_tree *t);
 // re-index if the unsorted tail has outgrown its limit
 void tree_prepare_query(rrtqx_tree *t);
