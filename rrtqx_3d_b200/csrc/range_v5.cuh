@@ -204,6 +204,17 @@ __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, uns
   }
 }
 
+// Trees with an unsorted tail (planner inserts since the last re-index) flush through an out-of-line copy, so the
+// hot path carries one flush body only.
+template <int D>
+__device__ __noinline__ void v5_flush_tail(const GridView *gp, const double *qs, unsigned sbuf_k, unsigned stab, int n,
+                                           int32_t *__restrict__ oi, double *__restrict__ od) {
+  double q[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) q[c] = qs[c];
+  v5_flush<D, true>(*gp, q, sbuf_k, stab, n, lane_id(), oi, od);
+}
+
 // Radius-dependent constants of the FP32 culling and filter (hoisted out of the pair loop when the
 // batch has one radius).
 struct V5Radius {
@@ -600,16 +611,22 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
         if (overflow) {
           v5_exact_query<D, true>(&s_g, qs, exactT(k), exactR(k), base, out_idx, out_dist);
         } else {
-          double q[D];
-#pragma unroll
-          for (int c = 0; c < D; ++c) q[c] = qs[c];
           const unsigned sb_k = sbuf + 2u * (unsigned)(k * CAP);
-          if (has_tail) v5_flush<D, true>(g, q, sb_k, stab, cnt, lane, out_idx + base, out_dist ? out_dist + base : nullptr);
-          else v5_flush<D, false>(g, q, sb_k, stab, cnt, lane, out_idx + base, out_dist ? out_dist + base : nullptr);
+          if (has_tail) {
+            v5_flush_tail<D>(&s_g, qs, sb_k, stab, cnt, out_idx + base, out_dist ? out_dist + base : nullptr);
+          } else {
+            double q[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) q[c] = qs[c];
+            v5_flush<D, false>(g, q, sb_k, stab, cnt, lane, out_idx + base, out_dist ? out_dist + base : nullptr);
+          }
         }
       };
-      emit(0, qs0, cnt0, (int64_t)b0, live0);
-      emit(1, qs1, cnt1, (int64_t)b0 + tot0, live1w);
+      // one copy of the flush code for both queries (the warps of a block run unsynchronised, so code
+      // size is instruction-cache pressure): a real loop, not two inlined bodies
+#pragma unroll 1
+      for (int k = 0; k < 2; ++k)
+        emit(k, k ? qs1 : qs0, k ? cnt1 : cnt0, (int64_t)b0 + (k ? tot0 : 0), k ? live1w : live0);
       if (root_extra && lane == 0) {  // the root at exactly distance r: appended behind the strict hits
         const double4 p0 = g.pos[0];
         if (root_extra & 1) {
