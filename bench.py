@@ -302,6 +302,22 @@ def c4_dubins(ctx, n_edges, steps):
             t_check.append(ctx.last_phase_ms("dubins_check"))
     _, rows = res.sizes()
     ms_s, ms_c = float(np.mean(t_solve)), float(np.mean(t_check))
+    # the kd side of C4: 200k nodes in [-50,50]^2 x {0} x [0,2pi), 4-D Euclid with the theta ghost identity
+    # (KDTree{T}(4, KDdist, [4], [2pi]), DRRT.jl:3312), 200k range queries at a radius giving E[k] ~ 16
+    import math
+    from rrtqx_3d_b200.device import DeviceTree, RangeResult
+    lo4, hi4 = [-50.0, -50.0, 0.0, 0.0], [50.0, 50.0, 0.0, 2.0 * math.pi]
+    nodes4 = W.uniform_points(4, 200_000, lo4, hi4)
+    q4 = torch.from_numpy(W.uniform_points(5, 200_000, lo4, hi4)).cuda()
+    t4 = DeviceTree(ctx, 4, wraps=[3], wrap_points=[2.0 * math.pi])
+    t4.insert_batch(nodes4)
+    r4res = RangeResult(ctx)
+    kd_ms = []
+    for it in range(3 + steps):
+        _, k4 = t4.range_query(q4, 1.06, result=r4res, n_queries=200_000)
+        if it >= 3:
+            kd_ms.append(ctx.last_phase_ms("range_query"))
+    kd_ms = float(np.mean(kd_ms))
     # CPU sample
     L = oracle.lib()
     f = lambda a: oracle._p(np.ascontiguousarray(a, dtype=np.float64), oracle.c_f64p)
@@ -330,7 +346,10 @@ def c4_dubins(ctx, n_edges, steps):
             "edges_per_s": n_edges / ((ms_s + ms_c) / 1e3), "colliding_edges": int(out.sum().item()),
             "cpu_edges_per_s": n_cpu / cpu_s, "cpu": f"oracle solver + check, 1 thread, first {n_cpu} edges "
                                                     "(python call overhead included)",
-            "algorithmic_bytes": n_edges * (64 + 16 + 1) + rows * 16 * 2}
+            "algorithmic_bytes": n_edges * (64 + 16 + 1) + rows * 16 * 2,
+            "kd_wrap_queries": {"nodes": 200_000, "queries": 200_000, "radius": 1.06, "mean_neighbours": k4 / 200_000,
+                                "ms": kd_ms, "queries_per_s": 200_000 / (kd_ms / 1e3),
+                                "note": "theta ghost identities run as (real, ghost) pairs of the range kernel"}}
 
 
 def c5_instances(ctx, rank, world, n_instances, n_iter):

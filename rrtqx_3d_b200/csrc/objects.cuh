@@ -23,6 +23,10 @@ struct rrtqx_range_result {
   int64_t qbins = 0;                        // bins of the last query sort (0: unsorted / iota order)
   rrtqx::DevBuf<double> tq;                  // per-query thresholds T_lt(r_q)
   rrtqx::DevBuf<unsigned long long> cursor;  // fused kernel: [0] output cursor, [1] chunk counter
+  // wrap-around trees through the pair kernel: virtual queries (real, ghost) and their per-identity results
+  rrtqx::DevBuf<double> vq;
+  rrtqx::DevBuf<int32_t> vorder, vcounts;
+  rrtqx::DevBuf<int64_t> voffsets;
 };
 
 struct rrtqx_edges {

@@ -337,7 +337,11 @@ static void range_query_impl(rrtqx_tree *t, const double *queries, int64_t nq, d
   res->counts.ensure((size_t)nq + 1, st);
   res->offsets.ensure((size_t)nq + 1, st);
   // the single-pass kernels pack (slot << 4 | count) into 32-bit octet-table entries: slots below 2^27
-  if (t->wrap.num_wraps == 0 && !getenv("RRTQX_RANGE_TWO_PASS") && t->n_sorted < ((int64_t)1 << 27)) {
+  // ... and wrap-around trees when the identities' hit sets are provably disjoint (one wrap dimension, one radius
+  // r <= period / 2: see ghost_expand_kernel); everything else takes the two-pass kernel with explicit dedup
+  const bool ghost_ok = t->wrap.num_wraps == 1 && !ranges && std::isfinite(r) && r > 0.0 &&
+                        r <= 0.5 * t->wrap.wrap_points[0] && nq < ((int64_t)1 << 29);
+  if ((t->wrap.num_wraps == 0 || ghost_ok) && !getenv("RRTQX_RANGE_TWO_PASS") && t->n_sorted < ((int64_t)1 << 27)) {
     range_query_fused<D>(t, dq, dr, nq, r, flags, res);
     return;
   }

@@ -451,6 +451,24 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     PhaseScope p2(ctx, "range_sort");
     sort_queries<D>(t, res, dq, nq);
   }
+  // wrap-around tree (one wrap dimension, r <= period / 2, checked by the caller): expand into (real, ghost) pairs
+  const bool ghost = t->wrap.num_wraps == 1;
+  const double *kq = dq, *kqs = res->qbins > 0 ? res->qsorted.p : nullptr;
+  const int32_t *korder = res->qorder.p;
+  int32_t *kcounts = res->counts.p;
+  int64_t *koffsets = res->offsets.p;
+  int64_t knq = nq;
+  if (ghost) {
+    res->vq.ensure((size_t)nq * 2 * D, st);
+    res->vorder.ensure((size_t)nq * 2, st);
+    res->vcounts.ensure((size_t)nq * 2 + 1, st);
+    res->voffsets.ensure((size_t)nq * 2 + 1, st);
+    // a point no candidate row can reach: beyond the grid along x by more than the radius
+    const double far0 = t->lo[0] - 4.0 * (std::fabs(r) + t->cell[0] * t->nx + 1.0) - std::fabs(t->lo[0]);
+    ghost_expand_kernel<D><<<div_up(nq, 256), 256, 0, st>>>(t->wrap, dq, kqs, res->qorder.p, nq, r, far0, res->vq.p, res->vorder.p);
+    post_launch(ctx);
+    kq = nullptr; kqs = res->vq.p; korder = res->vorder.p; kcounts = res->vcounts.p; koffsets = res->voffsets.p; knq = 2 * nq;
+  }
   const double T = host_sqrt_thresh_lt(r);
   const double *dT = nullptr;
   if (dr) {
@@ -498,9 +516,9 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
                              want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,             \
                              count_only ? 0 : 1)
 #define RQ_V5(NW_, CAP_, TAB_)                                                                                       \
-  launch_v5<D, NW_, CAP_, TAB_>(ctx, g, dq, res->qbins > 0 ? res->qsorted.p : nullptr, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
-                                want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p, count_only ? 0 : 1)
-      if (kernel_gen >= 5) {
+  launch_v5<D, NW_, CAP_, TAB_>(ctx, g, kq, kqs, korder, knq, r, T, dr, dT, kcounts, koffsets, res->idx.p, \
+                                want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p, count_only ? 0 : 1, ghost ? 1 : 0)
+      if (kernel_gen >= 5 || ghost) {
         // v5 (FP32 filter scan, packed exact records, 16-bit hit codes): hit buffers leave 32*V5_U entries of
         // head-room; the octet table must hold a whole pair's region (else the pair takes the exact routine)
         static const int v5_nw = [] { const char *e = getenv("RRTQX_V5_NW"); return e ? atoi(e) : 24; }();
@@ -526,6 +544,10 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     res->idx.ensure(cap, st, 0, 1.0);
     if (want_dist) res->dist.ensure(cap, st, 0, 1.0);
     cap = want_dist ? std::min(res->idx.cap, res->dist.cap) : res->idx.cap;
+  }
+  if (ghost) {
+    ghost_merge_kernel<<<div_up(nq, 256), 256, 0, st>>>(res->vcounts.p, res->voffsets.p, nq, res->counts.p, res->offsets.p);
+    post_launch(ctx);
   }
   res->n_queries = nq;
   res->total = (int64_t)total;

@@ -248,6 +248,7 @@ struct V5Params {
   V5Radius RU;
   float invx, invy, invz, celly, cellz;
   unsigned unit;  // pairs per dynamically scheduled unit of work
+  int ghost_pairs;  // 1: query 2j+1 is the ghost identity of query 2j (wrap-around trees): no root `<=` rule for it
 };
 
 // floor + clamp to [0, n-1] through the integer converter (F2I.FLOOR saturates, NaN -> 0): 3 instructions
@@ -340,13 +341,15 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
           if (c < D) {
             const double v = qs[c];
             qf[c] = __double2float_rn(c < 3 ? __dsub_rn(v, g.lo[c < 3 ? c : 0]) : v);
-            // fmaxf drops NaN: a NaN coordinate (the query can never hit) is caught by the != test
-            mab = fmaxf(mab, fabsf(qf[c]));
-            if (qf[c] != qf[c]) mab = INFINITY;
+            mab = fmaxf(mab, fabsf(qf[c]));  // fmaxf drops NaN; a NaN coordinate is flagged below
           } else {
             qf[c] = 0.0f;
           }
         }
+        // a NaN coordinate: the query can never hit (NaN < T is false in FP32 and FP64 alike), so it needs no
+        // rows and no exact path; flagged by mab = -1.  (Unused ghost identities of wrap-around trees arrive so.)
+#pragma unroll
+        for (int c = 0; c < D; ++c) if (qf[c] != qf[c]) mab = -1.0f;
       };
       // exact thresholds / radii for the rare exact paths (re-read, not kept in registers)
       auto exactT = [&](int k) { return uniform ? T_uniform : ((k == 0 || !have1) ? Tq[qid0] : Tq[qid1]); };
@@ -363,7 +366,7 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
         const double T0 = exactT(0), T1 = exactT(1);
         const double sr0 = sqdist<D>(q0, p0.x, p0.y, p0.z, p0.w), sr1 = sqdist<D>(q1, p0.x, p0.y, p0.z, p0.w);
         if (!(sr0 < T0) && sr0 <= T0 * 1.000001 && __dsqrt_rn(sr0) <= exactR(0)) root_extra |= 1;
-        if (have1 && !(sr1 < T1) && sr1 <= T1 * 1.000001 && __dsqrt_rn(sr1) <= exactR(1)) root_extra |= 2;
+        if (have1 && !P.ghost_pairs && !(sr1 < T1) && sr1 <= T1 * 1.000001 && __dsqrt_rn(sr1) <= exactR(1)) root_extra |= 2;
       }
       const bool live0 = R0.live, live1 = R1.live;
       bool exact_path = false;  // FP32 filter unusable, or the octet table overflowed
@@ -373,8 +376,9 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
         float qf0[4], qf1[4], mab0, mab1;
         fp32_query(qs0, qf0, mab0);
         fp32_query(qs1, qf1, mab1);
-        exact_path = !(fmaxabs + mab0 <= R0.sum_max) || !(fmaxabs + mab1 <= R1.sum_max);
-        if (!exact_path && g.n_sorted > 0) {
+        const bool rows0 = live0 && !(mab0 < 0.0f), rows1 = live1 && !(mab1 < 0.0f);
+        exact_path = (rows0 && !(fmaxabs + mab0 <= R0.sum_max)) || (rows1 && !(fmaxabs + mab1 <= R1.sum_max));
+        if (!exact_path && g.n_sorted > 0 && (rows0 || rows1)) {
           // cell coordinates (FP32; relative error 2^-23 per operation, nx <= 1024: far inside the 1e-3 cell slack)
           float ff0[3], ff1[3];
           ff0[0] = qf0[0] * invx; ff0[1] = qf0[1] * invy; ff0[2] = D >= 3 ? qf0[2] * invz : 0.0f;
@@ -384,11 +388,11 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
           const float rz0 = R0.rf * invz + 1e-3f, rz1 = R1.rf * invz + 1e-3f;
           int cy0 = 0x7fffffff, cy1 = -1, cz0 = 0, cz1 = 0;
           if (D >= 3) { cz0 = 0x7fffffff; cz1 = -1; }
-          if (live0) {
+          if (rows0) {
             cy0 = clampi_fast(ff0[1] - ry0, g.ny); cy1 = clampi_fast(ff0[1] + ry0, g.ny);
             if (D >= 3) { cz0 = clampi_fast(ff0[2] - rz0, g.nz); cz1 = clampi_fast(ff0[2] + rz0, g.nz); }
           }
-          if (live1) {
+          if (rows1) {
             cy0 = min(cy0, clampi_fast(ff1[1] - ry1, g.ny)); cy1 = max(cy1, clampi_fast(ff1[1] + ry1, g.ny));
             if (D >= 3) { cz0 = min(cz0, clampi_fast(ff1[2] - rz1, g.nz)); cz1 = max(cz1, clampi_fast(ff1[2] + rz1, g.nz)); }
           }
@@ -421,8 +425,8 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
                   cb = max(cb, clampi_fast(ff[0] + xc, g.nx));
                 }
               };
-              span(ff0, R0.r2f);
-              span(ff1, R1.r2f);
+              if (rows0) span(ff0, R0.r2f);
+              if (rows1) span(ff1, R1.r2f);
               if (cb >= ca) {
                 const int rbase = (cz * g.ny + cy) * g.nx;
                 sa_ = g.cell_start[rbase + ca];
@@ -649,11 +653,45 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
   }
 }
 
+// ---------------------------------------------------------------- wrap-around trees through the pair machinery
+// One wrap dimension (the Dubins heading, period 2 pi) and r <= period / 2: the hit sets of the real query and of
+// its ghost identity (ghostPoint.jl:60-111) are disjoint, so the reference's "first identity that reaches the node
+// wins" dedup (kdTree_general.jl:903-916) never fires and the result is the concatenation of the two sets.  The
+// batch is expanded into virtual queries 2j (real) and 2j+1 (ghost, or NaN -- a query that cannot hit -- when the ghost is
+// not used): exactly the pair a warp works on, whose two lists it writes back to back.
+template <int D>
+__global__ void ghost_expand_kernel(WrapInfo wrap, const double *__restrict__ queries, const double *__restrict__ qsorted,
+                                    const int32_t *__restrict__ qorder, int64_t nq, double r, double far0,
+                                    double *__restrict__ vq, int32_t *__restrict__ vorder) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nq) return;
+  const int qid = qorder[j];
+  const double *src = qsorted ? qsorted + j * D : queries + (int64_t)qid * D;
+  double q[D], gh[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) q[k] = src[k];
+  const bool used = make_ghost<D>(wrap, q, 1, r, gh);
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    vq[(2 * j) * D + k] = q[k];
+    vq[(2 * j + 1) * D + k] = used ? gh[k] : __longlong_as_double(0x7ff8000000000000LL);  // unused ghost: NaN, a dead query
+  }
+  vorder[2 * j] = 2 * qid;
+  vorder[2 * j + 1] = 2 * qid + 1;
+}
+__global__ void ghost_merge_kernel(const int32_t *__restrict__ vcounts, const int64_t *__restrict__ voffsets, int64_t nq,
+                                   int32_t *__restrict__ counts, int64_t *__restrict__ offsets) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  counts[q] = vcounts[2 * q] + vcounts[2 * q + 1];
+  offsets[q] = voffsets[2 * q];  // the pair's lists are contiguous: real identity first, then the ghost
+}
+
 template <int D, int NW, int CAP, int TAB>
 static void launch_v5(rrtqx_ctx *ctx, const GridView &g, const double *dq, const double *dqs, const int32_t *qorder,
                       int64_t nq, double r, double T, const double *dr, const double *dT, int32_t *counts,
                       int64_t *offsets, int32_t *idx, double *dist, unsigned long long cap, unsigned long long *cursor,
-                      int write_lists) {
+                      int write_lists, int ghost_pairs = 0) {
   const size_t smem = (size_t)NW * (CAP + TAB + V5_TABPAD) * sizeof(int);  // 16-bit hit codes: 2 * CAP * 2 bytes
   static bool attr_set = false;
   if (!attr_set) {
@@ -667,6 +705,7 @@ static void launch_v5(rrtqx_ctx *ctx, const GridView &g, const double *dq, const
   P.celly = (float)g.cell[1]; P.cellz = (float)g.cell[2];
   static const unsigned unit_env = [] { const char *e = getenv("RRTQX_V5_UNIT"); int v = e ? atoi(e) : 0; return (unsigned)(v > 0 ? v : 0); }();
   P.unit = unit_env ? unit_env : (unsigned)V5_UNIT;
+  P.ghost_pairs = ghost_pairs;
   const int64_t n_units = ((nq + 1) / 2 + P.unit - 1) / P.unit;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)ctx->sm_count));
   if (dr)

@@ -111,3 +111,31 @@ def test_other_dimensions_large_batch(ctx, d):
     qs = W.uniform_points(22, 2600, lo, hi)
     t, orc = _tree(ctx, pts, d)
     _check(t, orc, qs, 2.2 if d == 4 else 1.1, stride=11)
+
+
+def test_wrap_tree_through_ghost_pairs_large_batch(ctx):
+    """Dubins-style 4-D tree with theta wrapping (period 2 pi): for r <= pi the batch runs through the pair kernel as
+    (real, ghost) virtual queries; for r > pi through the two-pass kernel with explicit dedup.  Same sets and keys
+    as the reference's ghost iteration (ghostPoint.jl:60-111, kdTree_general.jl:903-916)."""
+    two_pi = 2.0 * np.pi
+    lo, hi = [-20.0, -20.0, 0.0, 0.0], [20.0, 20.0, 0.0, two_pi]
+    pts = W.uniform_points(31, 40000, lo, hi)
+    qs = W.uniform_points(32, 3000, lo, hi)
+    qs[:100, 3] = np.linspace(0.0, 0.2, 100)              # near the seam, both sides
+    qs[100:200, 3] = two_pi - np.linspace(0.0, 0.2, 100)
+    qs[200] = pts[0]                                       # on the root
+    qs[201, 3] = np.pi                                     # exactly at the ghost switch (q < P/2 is false)
+    orc = oracle.KDTree(4, wraps=[3], wrap_points=[two_pi])
+    orc.insert_batch(pts)
+    t = DeviceTree(ctx, 4, wraps=[3], wrap_points=[two_pi])
+    t.insert_batch(pts)
+    for r in (0.8, 2.0, 3.1, 3.3):                         # 3.3 > pi: two-pass path
+        _check(t, orc, qs, r, stride=3)
+    # odd batch, tiny batch, and a tail of single inserts
+    _check(t, orc, np.ascontiguousarray(qs[:2049]), 1.5, stride=11)
+    _check(t, orc, np.ascontiguousarray(qs[:3]), 1.5)
+    extra = W.uniform_points(33, 300, lo, hi)
+    for p in extra:
+        orc.insert(p)
+        t.insert(p)
+    _check(t, orc, qs, 2.0, stride=5)
