@@ -155,55 +155,70 @@ extend_query_kernel(GridView g, const ExtendParams prm, const double4 *__restric
   if (lane == 0) { s_best_s[warp] = bs; s_best_n[warp] = bn; }
   __syncthreads();
 
-  // ---- node check of p (thread 0, literal sequential semantics; DRRT_Q.jl:1520-1556 / 1558-1590) --
+  // ---- node check of p (DRRT_Q.jl:1520-1556 / 1558-1590), evaluated by warp 0 in parallel -------------
+  // The reference walks the list keeping retCert = running minimum of t_k = (dist_k - rho) - R_k, skips k
+  // when t_k > retCert and returns a collision at the first t_k < 0.  A skipped k can neither lower the
+  // minimum nor be negative (retCert >= 0 while no collision was found), and NaN never wins jl_min's `<`
+  // update, so: collision <=> any t_k < 0 (or, in the quick pass, any !(dist_k > R_k)); certificate = minimum
+  // of the non-NaN t_k.  Same values, evaluated by one lane per sphere.
   const int nsph = s_nsph;
-  if (tid == 0) {
+  if (warp == 0) {
     for (int w = 1; w < EXT_WARPS; ++w)
       if (s_best_s[w] < bs || (s_best_s[w] == bs && s_best_n[w] < bn)) { bs = s_best_s[w]; bn = s_best_n[w]; }
     bool hit = false;
-    if (prm.quick_pass)
-      for (int k = 0; k < nsph && !hit; ++k) {
+    double cert = INFINITY;
+    for (int k0 = 0; k0 < nsph; k0 += 32) {
+      const int k = k0 + lane;
+      if (k < nsph) {
         const double c[3] = {s_rec[k].x, s_rec[k].y, s_rec[k].z};
-        if (!(__dsqrt_rn(sqdist<3>(c, q[0], q[1], D >= 3 ? q[2] : 0.0, 0.0)) > s_rec[k].w)) hit = true;
+        const double dist = __dsqrt_rn(sqdist<3>(c, q[0], q[1], D >= 3 ? q[2] : 0.0, 0.0));
+        if (prm.quick_pass && !(dist > s_rec[k].w)) hit = true;
+        const double t = __dsub_rn(__dsub_rn(dist, rho), s_rec[k].w);
+        if (t < 0.0) hit = true;
+        if (t < cert) cert = t;
       }
-    double ret_cert = INFINITY;
-    for (int k = 0; k < nsph && !hit; ++k) {
-      const double c[3] = {s_rec[k].x, s_rec[k].y, s_rec[k].z};
-      double this_dist = __dsub_rn(__dsqrt_rn(sqdist<3>(c, q[0], q[1], D >= 3 ? q[2] : 0.0, 0.0)), rho);
-      if (__dsub_rn(this_dist, s_rec[k].w) > ret_cert) continue;
-      this_dist = __dsub_rn(this_dist, s_rec[k].w);
-      if (this_dist < 0.0) { hit = true; break; }
-      const double this_cert = jl_min(ret_cert, this_dist);
-      if (this_cert < ret_cert) ret_cert = this_cert;
     }
-    ExtendHeader h;
-    h.count = count;
-    h.nearest_idx = bn == 0x7fffffff ? -1 : bn;
-    h.nearest_dist = __dsqrt_rn(bs);
-    h.point_collides = hit ? 1 : 0;
-    h.overflow = count > prm.capacity ? 1 : 0;
-    h.cert = hit ? 0.0 : ret_cert;
-    *hdr = h;
+    hit = __any_sync(FULL, hit);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cert = fmin(cert, __shfl_xor_sync(FULL, cert, o));
+    if (lane == 0) {
+      ExtendHeader h;
+      h.count = count;
+      h.nearest_idx = bn == 0x7fffffff ? -1 : bn;
+      h.nearest_dist = __dsqrt_rn(bs);
+      h.point_collides = hit ? 1 : 0;
+      h.overflow = count > prm.capacity ? 1 : 0;
+      h.cert = hit ? 0.0 : cert;
+      *hdr = h;
+    }
   }
 
-  // ---- forward / reverse edge checks of every neighbour (SimpleEdge, 3-D); the finished entry goes
-  //      to the mapped host buffer with one 16-byte store (the host memory is never read back)
+  // ---- forward / reverse edge checks of every neighbour (SimpleEdge, 3-D): one thread per (neighbour,
+  //      direction); the even lane of each pair writes the finished entry to the mapped host buffer with
+  //      one 16-byte store (the host memory is never read back)
   const int m = min(count, prm.capacity);
-  for (int k = tid; k < m; k += blockDim.x) {
-    ExtendEntry e = ent[k];
-    if (D == 3) {
-      const double4 pn = g.pos[e.node];
-      const SegPre fwd = seg_prepare(q[0], q[1], q[2], pn.x, pn.y, pn.z);   // new -> neighbour
-      const SegPre rev = seg_prepare(pn.x, pn.y, pn.z, q[0], q[1], q[2]);   // neighbour -> new (not symmetric)
-      bool hf = false, hr = false;
-      for (int o = 0; o < nsph && !(hf && hr); ++o) {
-        if (!hf) hf = seg_sphere_collide<FMA_DOT>(fwd, s_rec[o].x, s_rec[o].y, s_rec[o].z, s_thr[o].x, s_thr[o].y);
-        if (!hr) hr = seg_sphere_collide<FMA_DOT>(rev, s_rec[o].x, s_rec[o].y, s_rec[o].z, s_thr[o].x, s_thr[o].y);
+  for (int t0 = 0; t0 < 2 * m; t0 += blockDim.x) {
+    const int t = t0 + tid, k = t >> 1;
+    const bool reverse = t & 1;
+    bool h = false;
+    ExtendEntry e;
+    e.node = 0; e.fwd = 0; e.rev = 0; e.pad = 0; e.dist = 0.0;
+    if (k < m) {
+      e = ent[k];
+      if (D == 3) {
+        const double4 pn = g.pos[e.node];
+        // new -> neighbour / neighbour -> new: the predicate is not symmetric in (start, end)
+        const SegPre seg = reverse ? seg_prepare(pn.x, pn.y, pn.z, q[0], q[1], q[2]) : seg_prepare(q[0], q[1], q[2], pn.x, pn.y, pn.z);
+        for (int o = 0; o < nsph && !h; ++o)
+          h = seg_sphere_collide<FMA_DOT>(seg, s_rec[o].x, s_rec[o].y, s_rec[o].z, s_thr[o].x, s_thr[o].y);
       }
-      e.fwd = hf ? 1 : 0;
-      e.rev = hr ? 1 : 0;
     }
-    ent_out[k] = e;
+    const bool h_other = __shfl_xor_sync(FULL, h, 1);
+    if (k < m && !reverse) {
+      e.fwd = h ? 1 : 0;
+      e.rev = h_other ? 1 : 0;
+      ent_out[k] = e;
+    }
   }
 }
 
