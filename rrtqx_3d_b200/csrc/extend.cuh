@@ -26,12 +26,14 @@ struct ExtendHeader {
   int32_t point_collides;
   int32_t overflow;
   double cert;
+  unsigned long long seq;  // written LAST by the kernel (after a system-scope fence): the host polls it
 };
 struct ExtendParams {
   double p[4];
   double r, T, rho;
   int32_t capacity;
   int32_t quick_pass, ignore_active, fma_dot;
+  unsigned long long seq;  // call number, echoed into the header when every result is visible to the host
 };
 
 template <int D, bool FMA_DOT>
@@ -189,6 +191,7 @@ extend_query_kernel(GridView g, const ExtendParams prm, const double4 *__restric
       h.point_collides = hit ? 1 : 0;
       h.overflow = count > prm.capacity ? 1 : 0;
       h.cert = hit ? 0.0 : cert;
+      h.seq = prm.seq - 1;  // the value the host still holds: unchanged until the completion store below
       *hdr = h;
     }
   }
@@ -220,6 +223,14 @@ extend_query_kernel(GridView g, const ExtendParams prm, const double4 *__restric
       ent_out[k] = e;
     }
   }
+  // completion: every thread's stores to the mapped host buffers are fenced to system scope, then one thread
+  // publishes the call number; the host spins on that word instead of paying a stream synchronisation
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    *(volatile unsigned long long *)&hdr->seq = prm.seq;
+    __threadfence_system();
+  }
 }
 
 struct ExtendState {   // per tree: mapped pinned result buffers + device scratch
@@ -227,6 +238,7 @@ struct ExtendState {   // per tree: mapped pinned result buffers + device scratc
   ExtendEntry *h_ent = nullptr, *d_ent_out = nullptr;  // mapped pinned
   DevBuf<ExtendEntry> scratch;
   int capacity = 0;
+  unsigned long long seq = 0;  // calls issued
   ~ExtendState() {
     if (h_hdr) cudaFreeHost(h_hdr);
     if (h_ent) cudaFreeHost(h_ent);
@@ -235,6 +247,7 @@ struct ExtendState {   // per tree: mapped pinned result buffers + device scratc
     if (!h_hdr) {
       RQ_CUDA(cudaHostAlloc((void **)&h_hdr, sizeof(ExtendHeader), cudaHostAllocMapped));
       RQ_CUDA(cudaHostGetDevicePointer((void **)&d_hdr, h_hdr, 0));
+      memset(h_hdr, 0, sizeof(ExtendHeader));
     }
     if (cap > capacity) {
       if (h_ent) { RQ_CUDA(cudaStreamSynchronize(st)); cudaFreeHost(h_ent); h_ent = nullptr; }
@@ -277,9 +290,10 @@ void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, do
   prm.quick_pass = (flags & RRTQX_CHECK_QUICK_PASS) ? 1 : 0;
   prm.ignore_active = (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0;
   prm.fma_dot = (flags & RRTQX_CHECK_FMA_DOT) ? 1 : 0;
+  prm.seq = ++es->seq;
   GridView g = t->view();
   {
-    PhaseScope ph(ctx, "extend_query");
+    // no phase events here: two event records would cost more host time than the kernel's launch
 #define RQ_EXT(D_, F_)                                                                                           \
   extend_query_kernel<D_, F_><<<1, EXT_WARPS * 32, 0, st>>>(g, prm, S->rec.p, S->active.p, (int)S->n, es->d_hdr, \
                                                             es->scratch.p, es->d_ent_out)
@@ -293,7 +307,20 @@ void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, do
 #undef RQ_EXT
     post_launch(ctx);
   }
-  RQ_CUDA(cudaStreamSynchronize(st));
+  // wait for the kernel's completion word (mapped pinned memory); a stream query every few thousand spins
+  // turns a faulted launch into an error instead of a hang
+  {
+    volatile unsigned long long *seqp = &es->h_hdr->seq;
+    for (unsigned spins = 0; *seqp != prm.seq; ++spins) {
+      if ((spins & 0xfff) == 0xfff) {
+        cudaError_t qe = cudaStreamQuery(st);
+        if (qe == cudaSuccess) break;  // kernel finished: the word is visible on the next read
+        if (qe != cudaErrorNotReady) RQ_CUDA(qe);
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (*seqp != prm.seq) RQ_CUDA(cudaStreamSynchronize(st));
+  }
   const ExtendHeader h = *es->h_hdr;
   if (nearest_idx) *nearest_idx = h.nearest_idx;
   if (nearest_dist) *nearest_dist = h.nearest_dist;

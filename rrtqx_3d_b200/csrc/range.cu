@@ -7,6 +7,7 @@
 // same s for every candidate the grid cannot exclude, and decide membership
 // with the sqrt-free but equivalent test s < T_lt(r).  sqrt is paid on hits
 // only (the returned JList key).
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
