@@ -121,3 +121,68 @@ def test_c3_full_size_sweep_is_union_of_single_obstacle_sweeps(ctx, c2):
                                       oracle._p(np.ascontiguousarray(dst[sample]), oracle.c_i32p), 0, len(sample),
                                       W.ROBOT_RADIUS, 0, oracle._p(want, oracle.c_u8p), 8)
     assert np.array_equal(flags[sample], want)
+
+
+def test_c4_full_size_wrap_queries_and_dubins(ctx):
+    """BASELINE config C4 at full size: 200k poses in [-50,50]^2 x {0} x [0,2pi), theta wrapping.
+    Range queries (ghost identities through the pair kernel): symmetry of the neighbour relation (q in N(p) <=>
+    p in N(q), also across the seam) on the whole batch + oracle sample; Dubins solver on 200k edges: oracle
+    sample at 1e-9 and the size-independent invariants (length >= chord, first row = start)."""
+    import math
+    from rrtqx_3d_b200.device import dubins_trajectory_batch
+    two_pi = 2.0 * math.pi
+    lo, hi = [-50.0, -50.0, 0.0, 0.0], [50.0, 50.0, 0.0, two_pi]
+    n = 200_000
+    pts = W.uniform_points(4, n, lo, hi)
+    t = DeviceTree(ctx, 4, wraps=[3], wrap_points=[two_pi])
+    t.insert_batch(pts)
+    r = 1.06
+    res, total = t.range_query(pts, r, want_dist=True)       # every node queries its own neighbourhood
+    counts, offsets = res.layout()
+    idx, dist = res.fetch()
+    assert total == counts.sum() and counts.min() >= 1       # every node finds itself (distance 0)
+    order = np.argsort(offsets, kind="stable")
+    src = np.empty(total, dtype=np.int64)
+    src[:] = np.repeat(order, counts[order])
+    # symmetric relation: the multiset of (min, max) pairs has every off-diagonal pair exactly twice
+    a, b = np.minimum(src, idx), np.maximum(src, idx)
+    off = a != b
+    key = a[off] * n + b[off]
+    uniq, cnt = np.unique(key, return_counts=True)
+    assert np.all(cnt == 2)
+    assert np.count_nonzero(~off) == n
+    # pairs across the seam exist (theta difference > pi but wrapped distance < r)
+    dth = np.abs(pts[src[off], 3] - pts[idx[off], 3])
+    assert np.count_nonzero(dth > math.pi) > 100
+    # oracle sample
+    orc = oracle.KDTree(4, wraps=[3], wrap_points=[two_pi])
+    orc.insert_batch(pts)
+    for q in range(0, n, 997):
+        oi, ok = orc.find_within_range(r, pts[q])
+        orc.empty(oi)
+        g = idx[offsets[q]:offsets[q] + counts[q]]
+        gd = dist[offsets[q]:offsets[q] + counts[q]]
+        go, oo = np.argsort(g, kind="stable"), np.argsort(oi, kind="stable")
+        assert np.array_equal(g[go], oi[oo])
+        assert np.array_equal(gd[go].view(np.uint64), ok[oo].view(np.uint64))
+    # Dubins edges between neighbours: 200k edges
+    e_src = src[off][:200_000]
+    e_dst = idx[off][:200_000].astype(np.int64)
+    s4, g4 = np.ascontiguousarray(pts[e_src]), np.ascontiguousarray(pts[e_dst])
+    dres = dubins_trajectory_batch(ctx, s4, g4, 1.0)
+    ddist, dtyp, dptr, dxy = dres.fetch()
+    chord = np.hypot(s4[:, 0] - g4[:, 0], s4[:, 1] - g4[:, 1])
+    ok_ = np.isfinite(ddist)
+    assert ok_.mean() > 0.99 and np.all(ddist[ok_] >= chord[ok_] - 1e-9)
+    first = dxy[dptr[:-1][ok_]]
+    assert np.allclose(first, s4[ok_, :2], atol=1e-9)
+    assert np.all((dtyp >= -1) & (dtyp <= 5))
+    for e in range(0, 200_000, 101):
+        od, ot, otr = oracle.dubins_trajectory(s4[e], g4[e], 1.0)
+        if not math.isfinite(od):
+            assert od == ddist[e] or (math.isnan(od) and math.isnan(ddist[e]))
+            continue
+        assert abs(od - ddist[e]) <= 1e-9 * max(1.0, od)
+        if ot == dtyp[e]:
+            tr = dxy[dptr[e]:dptr[e + 1]]
+            assert len(tr) == len(otr) and np.allclose(tr, otr, rtol=1e-9, atol=1e-9)
