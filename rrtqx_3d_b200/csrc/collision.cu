@@ -55,6 +55,7 @@ __global__ void sphere_table_kernel(const double4 *__restrict__ rec, const uint8
 struct SphereTableBufs {
   DevBuf<double4> rec, rec2;
   DevBuf<double2> thr, thr2;
+  DevBuf<float4> frec2;
   DevBuf<int32_t> id;
   DevBuf<int32_t> n;
   DevBuf<int32_t> cstart;
@@ -96,7 +97,7 @@ template <bool FMA_DOT, bool SRC_TREE>
 __global__ void __launch_bounds__(256)
 edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                        const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
-                       const double4 *__restrict__ rec, const double2 *__restrict__ thr,
+                       const double4 *__restrict__ rec, const double2 *__restrict__ thr, const float4 *__restrict__ frec,
                        const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ out) {
   __shared__ SphGrid G;
   if (threadIdx.x == 0) G = *Gp;
@@ -112,12 +113,13 @@ edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restric
     pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
   }
   const int ncell = G.nx * G.ny * G.nz;
+  const SegF32 sf = seg_f32(pre, G.cmax);
   bool hit = false;
   auto run = [&](int a, int b) {
     for (int o = a; o < b && !hit; ++o) {
+      if (seg_reject_f32(sf, frec[o])) continue;   // FP32 conservative reject: one 16-byte record
       const double4 r = rec[o];
-      const double2 t = thr[o];
-      hit = seg_sphere_collide<FMA_DOT>(pre, r.x, r.y, r.z, t.x, t.y);
+      hit = seg_sphere_collide_exact<FMA_DOT>(pre, r.x, r.y, r.z, thr[o].y);
     }
   };
   if (!pre.cullable) {
@@ -213,16 +215,17 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
       SphereTableBufs &b = table_bufs(ctx);
       b.rec2.ensure((size_t)spheres->n + 1, st);
       b.thr2.ensure((size_t)spheres->n + 1, st);
+      b.frec2.ensure((size_t)spheres->n + 1, st);
       b.cstart.ensure(SG_MAX_CELLS + 4, st);
       b.grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)b.grid.p;
-      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG);
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p);
       if (from_tree) {
-        if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
-        else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+        if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
+        else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
       } else {
-        if (fma) edge_check_grid_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
-        else     edge_check_grid_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.cstart.p, dG, dout);
+        if (fma) edge_check_grid_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
+        else     edge_check_grid_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
       }
       post_launch(ctx, 2);
     } else if (from_tree) {

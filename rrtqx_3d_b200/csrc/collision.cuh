@@ -86,6 +86,34 @@ __device__ __forceinline__ bool seg_sphere_collide(const SegPre &e, double px, d
   return !(s > thr_le);  // NaN radicand -> collides, as !(NaN > x) in the reference
 }
 
+// FP32 form of the conservative reject for the grid kernels (the reject is a filter: it may only say "cannot
+// collide" when that is certain).  u^ = fl32(c) - fl32(mid) differs from c - mid by at most
+// sqrt(3) 2^-24 (|c|max + |mid|max) + 2^-24 |u^| in norm; `bound` is three times the first term, the 1e-5 factors
+// cover the roundings of d2, lim and of thr / half (both rounded up).  Not cullable / not finite => never rejects.
+struct SegF32 {
+  float mx, my, mz, half, bound;
+  bool ok;
+};
+__device__ __forceinline__ SegF32 seg_f32(const SegPre &e, float cmax) {
+  SegF32 f;
+  f.mx = __double2float_rn(e.mx); f.my = __double2float_rn(e.my); f.mz = __double2float_rn(e.mz);
+  f.half = __double2float_ru(e.half);
+  f.bound = 3.0e-7f * (cmax + fmaxf(fabsf(f.mx), fmaxf(fabsf(f.my), fabsf(f.mz))));
+  f.ok = e.cullable && isfinite(f.bound) && isfinite(f.half);
+  return f;
+}
+__device__ __forceinline__ bool seg_reject_f32(const SegF32 &f, const float4 c /* centre, thr rounded up */) {
+  const float ux = c.x - f.mx, uy = c.y - f.my, uz = c.z - f.mz;
+  const float d2 = ux * ux + uy * uy + uz * uz;
+  const float lim = ((c.w + f.half) + f.bound) * 1.00001f;
+  return f.ok && d2 > lim * lim * 1.00001f;  // NaN anywhere: comparison false, no reject
+}
+// exact decision without the FP64 reject (the caller has run the FP32 one)
+template <bool FMA_DOT>
+__device__ __forceinline__ bool seg_sphere_collide_exact(const SegPre &e, double px, double py, double pz, double thr_le) {
+  return !(seg_point_radicand<FMA_DOT>(e, px, py, pz) > thr_le);
+}
+
 // ---------------------------------------------------------------- obstacle grid
 // For large edge batches the active-obstacle table is binned into a small uniform grid (cell >= 2 *
 // max(robotRadius + radius), at most 16^3 cells), so that an edge only meets the obstacles whose centre
@@ -98,6 +126,7 @@ struct SphGrid {
   int nx, ny, nz;  // cells; bucket nx*ny*nz is the "always" list
   double lo[3], inv[3];
   double thr_max;
+  float cmax;      // max |centre component| of the binned obstacles (error bound of the FP32 reject)
 };
 constexpr int SG_MAX_DIM = 16;
 constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
@@ -112,14 +141,15 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
                                           const double2 *__restrict__ extra /* optional payload */,
                                           const int32_t *__restrict__ n_live, int n_fixed, double4 *__restrict__ rec2,
                                           double2 *__restrict__ thr2, double2 *__restrict__ extra2,
-                                          int32_t *__restrict__ cstart, SphGrid *__restrict__ G) {
+                                          int32_t *__restrict__ cstart, SphGrid *__restrict__ G,
+                                          float4 *__restrict__ frec2 /* FP32 reject records, sorted order */) {
   __shared__ int hist[SG_MAX_CELLS + 2];
-  __shared__ double red[7][32];
+  __shared__ double red[8][32];
   __shared__ SphGrid g;
   const int n = n_live ? *n_live : n_fixed;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   // bounding box of the finite centres and the largest finite threshold
-  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, tm = 0.0;
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, tm = 0.0, cm = 0.0;
   for (int i = tid; i < n; i += blockDim.x) {
     const double4 r = rec[i];
     const double t = thr[i].x;
@@ -128,11 +158,12 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
       mn[1] = fmin(mn[1], r.y); mx[1] = fmax(mx[1], r.y);
       mn[2] = fmin(mn[2], r.z); mx[2] = fmax(mx[2], r.z);
       tm = fmax(tm, t);
+      cm = fmax(cm, fmax(fabs(r.x), fmax(fabs(r.y), fabs(r.z))));
     }
   }
-  double v[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], tm};
+  double v[8] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], tm, cm};
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < 8; ++k) {
     for (int o = 16; o > 0; o >>= 1) {
       const double w = __shfl_xor_sync(FULL, v[k], o);
       v[k] = k < 3 ? fmin(v[k], w) : fmax(v[k], w);
@@ -142,12 +173,13 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
   for (int i = tid; i < SG_MAX_CELLS + 2; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   if (tid == 0) {
-    double r7[7];
-    for (int k = 0; k < 7; ++k) {
+    double r7[8];
+    for (int k = 0; k < 8; ++k) {
       r7[k] = red[k][0];
       for (int w = 1; w < nw; ++w) r7[k] = k < 3 ? fmin(r7[k], red[k][w]) : fmax(r7[k], red[k][w]);
     }
     g.thr_max = r7[6];
+    g.cmax = __double2float_ru(r7[7]);
     g.n_total = n;
     int dims[3];
     for (int c = 0; c < 3; ++c) {
@@ -183,9 +215,13 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {
     const int o = atomicAdd(&hist[bucket(i)], 1);
-    rec2[o] = rec[i];
+    const double4 rr = rec[i];
+    rec2[o] = rr;
     thr2[o] = thr[i];
     if (extra) extra2[o] = extra[i];
+    if (frec2)  // non-finite obstacles (the "always" bucket) get NaN / Inf here: never rejected
+      frec2[o] = make_float4(__double2float_rn(rr.x), __double2float_rn(rr.y), __double2float_rn(rr.z),
+                             __double2float_ru(thr[i].x));
   }
 }
 

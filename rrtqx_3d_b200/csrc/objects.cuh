@@ -57,6 +57,7 @@ struct rrtqx_sweep_result {
   rrtqx::DevBuf<double4> ob_par;  // (thr, thr_le, search_T_lt, search_range)
   rrtqx::DevBuf<double2> ob_thr, ob_ext, ob_thr2, ob_ext2;  // (thr, thr_le) / (T_lt(searchRange), searchRange)
   rrtqx::DevBuf<double4> ob_rec2;
+  rrtqx::DevBuf<float4> ob_frec2;  // FP32 reject records of the binned obstacles
   rrtqx::DevBuf<int32_t> cstart;
   rrtqx::DevBuf<unsigned char> grid;
   rrtqx::DevBuf<int32_t> ids_stage, ids_stage2;

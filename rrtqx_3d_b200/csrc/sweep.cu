@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(256)
 add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src,
                       const int32_t *__restrict__ dst, int64_t n_edges, const int32_t *__restrict__ parent,
                       const double4 *__restrict__ rec, const double2 *__restrict__ thr, const double2 *__restrict__ ext,
-                      const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ edge_flag,
-                      uint8_t *__restrict__ node_flag) {
+                      const float4 *__restrict__ frec, const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp,
+                      uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag) {
   __shared__ SphGrid G;
   if (threadIdx.x == 0) G = *Gp;
   __syncthreads();
@@ -333,12 +333,13 @@ add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const in
   }
   const double4 a = pos[v], b = pos[w];
   const SegPre pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+  const SegF32 sf = seg_f32(pre, G.cmax);
   bool hit = false;
   auto run = [&](int lo, int hi) {
     for (int o = lo; o < hi && !hit; ++o) {
+      if (seg_reject_f32(sf, frec[o])) continue;   // FP32 conservative reject: one 16-byte record
       const double4 r = rec[o];
-      const double2 t = thr[o];
-      if (seg_sphere_collide<FMA_DOT>(pre, r.x, r.y, r.z, t.x, t.y)) {
+      if (seg_sphere_collide_exact<FMA_DOT>(pre, r.x, r.y, r.z, thr[o].y)) {
         const double q[3] = {r.x, r.y, r.z};
         const double s = sqdist<3>(q, a.x, a.y, a.z, 0.0);  // euclid(ob.position, startNode.position)
         const double2 e = ext[o];
@@ -496,17 +497,18 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       R->cstart.ensure(SG_MAX_CELLS + 4, st);
       R->grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)R->grid.p;
+      R->ob_frec2.ensure((size_t)n_obs + 1, st);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
-                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG);
+                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p);
       const int64_t work = E->n_edges + E->n_nodes;
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
       if (flags & RRTQX_CHECK_FMA_DOT)
         add_sweep_edge_kernel<true><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
-                                                                     R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG,
+                                                                     R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->ob_frec2.p, R->cstart.p, dG,
                                                                      R->edge_flag.p, R->node_flag.p);
       else
         add_sweep_edge_kernel<false><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
-                                                                      R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG,
+                                                                      R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->ob_frec2.p, R->cstart.p, dG,
                                                                       R->edge_flag.p, R->node_flag.p);
       post_launch(ctx, 3);
       no_stats = true;
