@@ -463,9 +463,7 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     res->vorder.ensure((size_t)nq * 2, st);
     res->vcounts.ensure((size_t)nq * 2 + 1, st);
     res->voffsets.ensure((size_t)nq * 2 + 1, st);
-    // a point no candidate row can reach: beyond the grid along x by more than the radius
-    const double far0 = t->lo[0] - 4.0 * (std::fabs(r) + t->cell[0] * t->nx + 1.0) - std::fabs(t->lo[0]);
-    ghost_expand_kernel<D><<<div_up(nq, 256), 256, 0, st>>>(t->wrap, dq, kqs, res->qorder.p, nq, r, far0, res->vq.p, res->vorder.p);
+    ghost_expand_kernel<D><<<div_up(nq, 256), 256, 0, st>>>(t->wrap, dq, kqs, res->qorder.p, nq, r, res->vq.p, res->vorder.p);
     post_launch(ctx);
     kq = nullptr; kqs = res->vq.p; korder = res->vorder.p; kcounts = res->vcounts.p; koffsets = res->voffsets.p; knq = 2 * nq;
   }

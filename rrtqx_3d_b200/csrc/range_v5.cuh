@@ -661,7 +661,7 @@ range_v5_kernel(GridView g_param, V5Params P, const double *__restrict__ queries
 // not used): exactly the pair a warp works on, whose two lists it writes back to back.
 template <int D>
 __global__ void ghost_expand_kernel(WrapInfo wrap, const double *__restrict__ queries, const double *__restrict__ qsorted,
-                                    const int32_t *__restrict__ qorder, int64_t nq, double r, double far0,
+                                    const int32_t *__restrict__ qorder, int64_t nq, double r,
                                     double *__restrict__ vq, int32_t *__restrict__ vorder) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nq) return;
