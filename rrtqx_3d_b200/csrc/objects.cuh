@@ -21,6 +21,7 @@ struct rrtqx_range_result {
   rrtqx::DevBuf<int64_t> scan_tmp64;
   rrtqx::DevBuf<double> qsorted;             // query coordinates in sorted order (valid when qbins > 0)
   int64_t qbins = 0;                        // bins of the last query sort (0: unsorted / iota order)
+  bool qhist_clean = false;                 // qhist is all-zero (left so by the last complete sort)
   rrtqx::DevBuf<double> tq;                  // per-query thresholds T_lt(r_q)
   rrtqx::DevBuf<unsigned long long> cursor;  // fused kernel: [0] output cursor, [1] chunk counter
   // wrap-around trees through the pair kernel: virtual queries (real, ghost) and their per-identity results

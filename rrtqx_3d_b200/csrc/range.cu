@@ -43,14 +43,16 @@ __global__ void query_key_kernel(GridView g, int S, int F, int nsx, int nsy, con
 
 // Scatter into sorted order; also writes the query coordinates in sorted order so that the range
 // kernel reads its queries with coalesced, L1-friendly loads (one dependent load less per group).
+// `hist` still holds the bin counts of the key pass: every query takes the slot start[c] + (old count - 1) and
+// counts its bin down, so the histogram is all-zero again when the kernel ends (no memset before the next sort).
 template <int D>
 __global__ void query_scatter_kernel(const int32_t *__restrict__ key, const double *__restrict__ q, int64_t nq,
-                                     const int32_t *__restrict__ start, int32_t *__restrict__ cursor,
+                                     const int32_t *__restrict__ start, int32_t *__restrict__ hist,
                                      int32_t *__restrict__ order, double *__restrict__ qsorted) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   int c = key[i];
-  const int pos = start[c] + atomicAdd(&cursor[c], 1);
+  const int pos = start[c] + atomicSub(&hist[c], 1) - 1;
   order[pos] = (int32_t)i;
 #pragma unroll
   for (int k = 0; k < D; ++k) qsorted[(int64_t)pos * D + k] = q[i * D + k];
@@ -82,17 +84,21 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   r->qbins = nbins;
   const int ncell = (int)nbins;
   r->qkey.ensure((size_t)nq, st);
+  // the histogram is self-cleaning (query_scatter_kernel counts it back to zero): zero it only when the buffer is
+  // new or a previous sort did not run to its end
+  const bool fresh = r->qhist.cap < (size_t)ncell + 1 || !r->qhist_clean;
   r->qhist.ensure((size_t)ncell + 1, st);
   r->qstart.ensure((size_t)ncell + 1, st);
-  RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
+  if (fresh) RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * r->qhist.cap, st));
+  r->qhist_clean = false;
   GridView g = t->view();
   query_key_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(g, S, F, nsx, nsy, dq, nq, r->qkey.p, r->qhist.p);
   post_launch(ctx);
   exclusive_scan<int32_t, int32_t>(ctx, r->qhist.p, ncell, r->qstart.p, r->scan_tmp32);
-  RQ_CUDA(cudaMemsetAsync(r->qhist.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   r->qsorted.ensure((size_t)nq * D, st);
   query_scatter_kernel<D><<<div_up(nq, TB), TB, 0, st>>>(r->qkey.p, dq, nq, r->qstart.p, r->qhist.p, r->qorder.p, r->qsorted.p);
   post_launch(ctx);
+  r->qhist_clean = true;
 }
 
 // --------------------------------------------------------- query identities
