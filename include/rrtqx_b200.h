@@ -106,7 +106,10 @@ RRTQX_API rrtqx_status rrtqx_tree_insert_batch(rrtqx_tree *tree,
                                                const double *positions,
                                                int64_t n,
                                                int32_t *first_index_out);
-/* kdInsert of one node (the planner's per-iteration insert, DRRT_Q.jl:2575). */
+/* kdInsert of one node (the planner's per-iteration insert, DRRT_Q.jl:2575).
+ * A host position is read during the call and inserted by ONE asynchronous
+ * launch (position passed by value): the call does not wait for the device;
+ * every later call on the same context sees the node (stream order). */
 RRTQX_API rrtqx_status rrtqx_tree_insert(rrtqx_tree *tree,
                                          const double *position,
                                          int32_t *index_out);
