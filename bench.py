@@ -527,6 +527,26 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps}
 
+    # ------------------------------------------------------- extra: sparse variant: index cost vs output cost
+    try:
+        sp_r = 0.7795
+        sp = []
+        res_sp = RangeResult(ctx)
+        for it in range(3 + max(3, min(args.steps, 10))):
+            flush.zero_()
+            _, k_sp = tree.range_query(dq, sp_r, want_dist=True, result=res_sp, n_queries=args.queries)
+            if it >= 3:
+                sp.append(ctx.last_phase_ms("range_query"))
+        sp_ms = float(np.mean(sp))
+        sp_bytes = args.nodes * 24 + args.queries * 24 + (args.queries + 1) * 8 + k_sp * 12
+        line["sparse_variant"] = {"radius": sp_r, "mean_neighbours": k_sp / args.queries, "ms": sp_ms,
+                                  "queries_per_s": args.queries / (sp_ms / 1e3), "algorithmic_bytes": sp_bytes,
+                                  "hbm_frac": sp_bytes / (sp_ms / 1e3) / 1e9 / peak_gbs,
+                                  "note": "same tree and queries at a radius with ~30 neighbours: set-up + rows dominate"}
+        res_sp.close()
+    except Exception as exc:
+        line["sparse_variant"] = {"error": repr(exc)}
+
     # ------------------------------------------------------- extra: batched kdFindNearest on the same workload
     try:
         nn_idx = torch.empty(args.queries, dtype=torch.int32, device="cuda")
