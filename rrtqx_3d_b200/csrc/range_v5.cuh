@@ -185,23 +185,30 @@ __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, uns
       if (od) od[h0 + 32 * u] = __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w));
     }
   }
-  if (n_full < n) {  // last, partial group: same shape (all loads in flight before the first use), predicated
+  // last, partial group: same shape (all loads in flight before the first use), predicated, and only as many rows
+  // as the remainder needs (1, 2 or 4): a short list does not pay for four rows of FP64 work
+  auto tail = [&](auto rows_tag) {
+    constexpr int R = decltype(rows_tag)::value;
     const int h0 = n_full + lane;
-    int node[U];
-    double4 p[U];
+    int node[R];
+    double4 p[R];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < R; ++u) {
       // lanes past the end re-read hit 0 (always present here): no predicated loads, only predicated stores
       const int hh = h0 + 32 * u < n ? h0 + 32 * u : 0;
       fetch(lds16(sbuf_k + 2u * (unsigned)hh), node[u], p[u]);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < R; ++u)
       if (h0 + 32 * u < n) {
         oi[h0 + 32 * u] = node[u];
         if (od) od[h0 + 32 * u] = __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w));
       }
-  }
+  };
+  const int rem = n - n_full;
+  if (rem > 64) tail(std::integral_constant<int, 4>{});
+  else if (rem > 32) tail(std::integral_constant<int, 2>{});
+  else if (rem > 0) tail(std::integral_constant<int, 1>{});
 }
 
 // Trees with an unsorted tail (planner inserts since the last re-index) flush through an out-of-line copy, so the
