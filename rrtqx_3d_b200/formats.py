@@ -166,6 +166,48 @@ def save_obstacle_locations(fp, centers, radii, unused, expired=None) -> None:
     writedlm_rows(fp, np.column_stack([centers[keep], radii[keep]]))
 
 
+def save_rrt_nodes_collision(fp, positions, order, tree_cost, lmc) -> None:
+    """saveRRTNodesCollision (DRRT_Q.jl:340-362): [position min(rrtTreeCost, rrtLMC)] per node in kd visit order.
+    Julia's `min` propagates NaN (either operand), unlike np.minimum's ordering of signed zeros only."""
+    positions = np.asarray(positions, dtype=np.float64)
+    a, b = np.asarray(tree_cost, dtype=np.float64)[order], np.asarray(lmc, dtype=np.float64)[order]
+    writedlm_rows(fp, np.column_stack([positions[order], np.minimum(a, b)]))   # np.minimum propagates NaN too
+
+
+def save_data(fp, data) -> None:
+    """saveData (DRRT_Q.jl:41-48): every row of a matrix as one comma-separated line (robotMovePath dumps,
+    rrtqx.jl:879)."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.size:
+        writedlm_rows(fp, data.reshape(data.shape[0], -1))
+
+
+def save_rrt_path_q(fp, positions, node, root, parent, parent_used=None, trajectories=None, max_hops=1000) -> None:
+    """saveRRTPath_Q (DRRT_Q.jl:3880-3891): follow parent edges from `node` while the node is not the root, its
+    parent edge is in use and fewer than 1000 hops were taken; each hop writes saveEdgeTrajectory of the parent edge
+    (SimpleEdge: start row then end row, DRRT_SimpleEdge_functions.jl:193-196; DubinsEdge: the trajectory rows,
+    DRRT_DubinsEdge_functions.jl:734-736 - pass `trajectories`, a callable node -> rows of its parent edge);
+    finally the first three coordinates of the node reached."""
+    positions = np.asarray(positions, dtype=np.float64)
+    parent = np.asarray(parent)
+    used = (parent >= 0) if parent_used is None else np.asarray(parent_used, dtype=bool)
+    this, hops = int(node), 0
+    while this != root and used[this] and hops < max_hops:
+        if trajectories is None:
+            writedlm_rows(fp, positions[[this, int(parent[this])]])
+        else:
+            writedlm_rows(fp, trajectories(this))
+        this = int(parent[this])
+        hops += 1
+    writedlm_rows(fp, positions[this, :3])
+
+
+def save_kds_q(fp, kino_dist, aug_dist) -> None:
+    """saveKds_Q (DRRT_Q.jl:3873-3878): the two scalars, one per line (writedlm of a scalar)."""
+    fp.write(julia_float(kino_dist) + "\n")
+    fp.write(julia_float(aug_dist) + "\n")
+
+
 def dump_to_string(writer, *args, **kw) -> str:
     buf = io.StringIO()
     writer(buf, *args, **kw)

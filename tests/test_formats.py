@@ -72,3 +72,27 @@ def test_dump_writers():
     assert F.dump_to_string(F.save_rrt_graph, pos, order, row_ptr, col) == (
         "0.0,0.0,0.0\n1.0,2.0,3.0\n0.0,0.0,0.0\n-1.5,0.25,1.0e-5\n1.0,2.0,3.0\n0.0,0.0,0.0\n4.0,5.0,6.0\n1.0,2.0,3.0\n")
     assert F.dump_to_string(F.save_obstacle_locations, [[1, 2, 3], [4, 5, 6]], [3.5, 1.0], [False, True]) == "1.0,2.0,3.0,3.5\n"
+
+
+def test_path_kd_data_and_collision_node_writers():
+    pos = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 3.0], [4.5, -1.0, 2.0], [7.0, 7.0, 7.0]])
+    parent = np.array([-1, 0, 1, 2])
+    out = F.dump_to_string(F.save_rrt_path_q, pos, 3, 0, parent)
+    assert out == ("7.0,7.0,7.0\n4.5,-1.0,2.0\n" "4.5,-1.0,2.0\n1.0,2.0,3.0\n" "1.0,2.0,3.0\n0.0,0.0,0.0\n" "0.0,0.0,0.0\n")
+    # a node whose parent edge is not in use ends the walk there (rrtParentUsed false)
+    out = F.dump_to_string(F.save_rrt_path_q, pos, 3, 0, parent, parent_used=[False, True, False, True])
+    assert out == "7.0,7.0,7.0\n4.5,-1.0,2.0\n4.5,-1.0,2.0\n"
+    # the hop limit of the reference (i < 1000) on a parent cycle
+    cyc = np.array([-1, 2, 1])
+    out = F.dump_to_string(F.save_rrt_path_q, pos[:3], 1, 0, cyc)
+    assert out.count("\n") == 2 * 1000 + 1
+    # Dubins edges write their trajectory rows
+    traj = {1: np.array([[1.0, 2.0], [0.5, 1.0], [0.0, 0.0]])}
+    out = F.dump_to_string(F.save_rrt_path_q, pos, 1, 0, parent, trajectories=lambda n: traj[n])
+    assert out == "1.0,2.0\n0.5,1.0\n0.0,0.0\n0.0,0.0,0.0\n"
+    assert F.dump_to_string(F.save_kds_q, 0.25, 1.0e-5) == "0.25\n1.0e-5\n"
+    assert F.dump_to_string(F.save_data, np.array([[1.0, 2.5], [3.0, 1e7]])) == "1.0,2.5\n3.0,1.0e7\n"
+    assert F.dump_to_string(F.save_data, np.zeros((0, 3))) == ""
+    order = np.array([0, 2, 1])
+    out = F.dump_to_string(F.save_rrt_nodes_collision, pos[:3], order, [0.0, np.inf, 2.0], [1.0, 5.0, np.nan])
+    assert out == "0.0,0.0,0.0,0.0\n4.5,-1.0,2.0,NaN\n1.0,2.0,3.0,5.0\n"
