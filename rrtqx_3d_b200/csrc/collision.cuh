@@ -127,9 +127,20 @@ struct SphGrid {
   double lo[3], inv[3];
   double thr_max;
   float cmax;      // max |centre component| of the binned obstacles (error bound of the FP32 reject)
+  double hi[3];    // upper corner of the box of the finite centres (lo[] is the lower one when binned)
+  // Cover lists for short edges (collide_queue.cuh): a fine grid whose cell c lists every binned obstacle o
+  // with dist(c_o, box(c)) <= thr_o + cov_cap, so an edge with half length <= cov_cap only meets the list of
+  // the cell that holds its midpoint.  cov_on = 0: not built / over budget, use the coarse rows.
+  int cov_on;
+  int cnx, cny, cnz;
+  double clo[3], cinv[3], ccell[3];
+  double cov_cap, cov_margin;
 };
 constexpr int SG_MAX_DIM = 16;
 constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
+constexpr int COV_DIM = 32;
+constexpr int COV_CELLS = COV_DIM * COV_DIM * COV_DIM;
+constexpr int COV_BUDGET = 1 << 21;  // entries of all cover lists together; above it the cover is switched off
 
 __device__ __forceinline__ int sg_cell(double v, double lo, double inv, int n) {
   double c = floor((v - lo) * inv);
@@ -142,7 +153,8 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
                                           const int32_t *__restrict__ n_live, int n_fixed, double4 *__restrict__ rec2,
                                           double2 *__restrict__ thr2, double2 *__restrict__ extra2,
                                           int32_t *__restrict__ cstart, SphGrid *__restrict__ G,
-                                          float4 *__restrict__ frec2 /* FP32 reject records, sorted order */) {
+                                          float4 *__restrict__ frec2 /* FP32 reject records, sorted order */,
+                                          int cover = 0 /* also set up the cover grid (collide_queue.cuh) */) {
   __shared__ int hist[SG_MAX_CELLS + 2];
   __shared__ double red[8][32];
   __shared__ SphGrid g;
@@ -194,6 +206,30 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
       }
     }
     g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    // cover grid: the box of the centres grown by 1.25 thr_max, COV_DIM cells per dimension
+    g.cov_on = 0;
+    g.cnx = g.cny = g.cnz = 1;
+    g.cov_cap = 0.0;
+    g.cov_margin = 0.0;
+    double cap = INFINITY, span = 0.0;
+    bool ok = g.thr_max > 0.0;
+    for (int c = 0; c < 3; ++c) {
+      g.hi[c] = r7[3 + c];
+      const double pad = 1.25 * g.thr_max;
+      const double lo2 = r7[c] - pad, ext2 = (r7[3 + c] - r7[c]) + 2.0 * pad;
+      ok = ok && isfinite(lo2) && isfinite(ext2) && ext2 > 0.0;
+      g.clo[c] = lo2;
+      g.ccell[c] = ext2 / COV_DIM;
+      g.cinv[c] = COV_DIM / ext2;
+      cap = fmin(cap, 0.5 * g.ccell[c]);
+      span = fmax(span, ext2);
+    }
+    if (ok && isfinite(cap) && cap > 0.0 && isfinite(g.cinv[0]) && isfinite(g.cinv[1]) && isfinite(g.cinv[2])) {
+      g.cov_on = cover ? 1 : 0;
+      g.cnx = g.cny = g.cnz = COV_DIM;
+      g.cov_cap = cap;
+      g.cov_margin = 1e-9 * (r7[7] + span + g.thr_max);
+    }
     *G = g;
   }
   __syncthreads();

@@ -6,6 +6,7 @@
 // surgery (edge.dist = Inf, orphaning, queue pushes) to the returned id sets.
 #include "objects.cuh"
 #include "scan.cuh"
+#include "collide_queue.cuh"
 
 namespace rrtqx {
 
@@ -367,6 +368,55 @@ add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const in
   }
 }
 
+// The same sweep in warp-queue form (collide_queue.cuh): items are the out-edges followed by one parent edge
+// per node; a colliding (edge, obstacle) pair counts only if the edge's start node passes the obstacle's
+// start-node filter.
+struct SweepEdgeSrc {
+  const double4 *pos;
+  int64_t n_edges;
+  const int32_t *src, *dst, *parent;
+  const double2 *ext;
+  uint8_t *edge_flag, *node_flag;
+  __device__ __forceinline__ bool endpoints(int64_t i, double a[3], double b[3], int &v) const {
+    int w;
+    if (i >= n_edges) {
+      v = (int)(i - n_edges);
+      w = parent ? parent[v] : -1;
+      if (w < 0) return false;
+    } else {
+      v = src[i];
+      w = dst[i];
+    }
+    const double4 pa = pos[v], pb = pos[w];
+    a[0] = pa.x; a[1] = pa.y; a[2] = pa.z;
+    b[0] = pb.x; b[1] = pb.y; b[2] = pb.z;
+    return true;
+  }
+  __device__ __forceinline__ void clear(int64_t) const {}  // flags are zeroed by prepare_result
+  __device__ __forceinline__ bool accept(int o, const double4 &r, const double a[3], int v) const {
+    const double q[3] = {r.x, r.y, r.z};
+    const double s = sqdist<3>(q, a[0], a[1], a[2], 0.0);  // euclid(ob.position, startNode.position)
+    const double2 e = ext[o];
+    return (s < e.x) || (v == 0 && __dsqrt_rn(s) <= e.y);
+  }
+  __device__ __forceinline__ void mark(int64_t i) const {
+    if (i >= n_edges) node_flag[i - n_edges] = 1; else edge_flag[i] = 1;
+  }
+};
+
+template <bool FMA_DOT>
+__global__ void __launch_bounds__(256)
+add_sweep_queue_kernel(SweepEdgeSrc S, int64_t n_items, const double4 *__restrict__ rec, const double2 *__restrict__ thr,
+                       const float4 *__restrict__ frec, const int32_t *__restrict__ cstart,
+                       const int32_t *__restrict__ cov_start, const int32_t *__restrict__ cov_list,
+                       const SphGrid *__restrict__ Gp) {
+  __shared__ SphGrid G;
+  __shared__ int2 queue[8][CQ_CAP];
+  if (threadIdx.x == 0) G = *Gp;
+  __syncthreads();
+  cq_run<FMA_DOT>(S, n_items, G, rec, thr, frec, cstart, cov_start, cov_list, queue[threadIdx.x >> 5]);
+}
+
 // removeObstacle: one thread per edge (upload order).  ob = table entry 0,
 // others = entries 1..n_tab-1 (thr / thr_le only).
 template <bool FMA_DOT>
@@ -498,11 +548,21 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       R->grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)R->grid.p;
       R->ob_frec2.ensure((size_t)n_obs + 1, st);
-      sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
-                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p);
       const int64_t work = E->n_edges + E->n_nodes;
+      const bool use_queue = work >= cover_min_items();
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
+                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, use_queue ? 1 : 0);
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
-      if (flags & RRTQX_CHECK_FMA_DOT)
+      if (use_queue) {
+        SphCoverBufs &cv = cover_bufs(ctx);
+        build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->cstart.p, dG, (int)n_obs);
+        SweepEdgeSrc Q{E->tree->pos.p, E->n_edges, E->src.p, E->dst.p, par, R->ob_ext2.p, R->edge_flag.p, R->node_flag.p};
+        const unsigned qblocks = (unsigned)div_up(div_up(work, (int64_t)32 * CQ_BATCHES), (int64_t)(TB / 32));
+        if (flags & RRTQX_CHECK_FMA_DOT)
+          add_sweep_queue_kernel<true><<<qblocks, TB, 0, st>>>(Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, cv.start.p, cv.list.p, dG);
+        else
+          add_sweep_queue_kernel<false><<<qblocks, TB, 0, st>>>(Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, cv.start.p, cv.list.p, dG);
+      } else if (flags & RRTQX_CHECK_FMA_DOT)
         add_sweep_edge_kernel<true><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
                                                                      R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->ob_frec2.p, R->cstart.p, dG,
                                                                      R->edge_flag.p, R->node_flag.p);

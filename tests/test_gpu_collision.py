@@ -316,3 +316,42 @@ def test_resident_edge_set_grows_with_the_planner(ctx):
     st = E.add_sweep(S, ob_ids, W.ROBOT_RADIUS, W.DELTA, flags=A.SWEEP_STATS)
     se, sn = st.fetch()
     assert np.array_equal(se, got_e) and np.array_equal(sn, got_n)
+
+
+def test_edge_check_cover_lists_short_edges(ctx):
+    """Large batches of SHORT edges take the warp-queue kernel with cover lists (csrc/collide_queue.cuh): one
+    fine-grid cell list per edge instead of the coarse rows.  Mixed with long, zero-length and out-of-box edges,
+    against obstacle sets that keep the cover (C3-style), overflow its budget (huge spheres: coarse rows), are
+    tiny compared with the box, or sit outside the tree's box; booleans bit-exact, with and without the FMA dot."""
+    pts, _, _ = W.c2_workload(30000, 1)
+    t, src, dst, _ = _neighbour_graph(ctx, pts, 1.3)
+    assert len(src) > 100000
+    src, dst = src.copy(), dst.copy()
+    dst[::97] = src[::97]                                    # zero-length edges
+    dst[5::101] = (src[5::101] + 7777) % len(pts)            # long edges (coarse rows)
+    far = np.array([[1e3, 1e3, 1e3], [1e3 + 0.2, 1e3, 1e3 + 0.1], [-500.0, 3.0, 2.0], [-500.1, 3.2, 2.0]])
+    n0 = len(pts)
+    pts2 = np.ascontiguousarray(np.vstack([pts, far]))       # short edges far outside the obstacle box
+    t2 = DeviceTree(ctx, 3)
+    t2.insert_batch(pts2)
+    src = np.concatenate([src, np.array([n0, n0 + 1, n0 + 2, n0 + 3], dtype=np.int32)])
+    dst = np.concatenate([dst, np.array([n0 + 1, n0, n0 + 3, n0 + 2], dtype=np.int32)])
+    rng = np.random.default_rng(5)
+    sets = {
+        "c3": W.c3_obstacles(256),
+        "huge": (rng.uniform(-20, 20, (3000, 3)), rng.uniform(10.0, 15.0, 3000)),        # cover over budget
+        "tiny": (rng.uniform(-20, 20, (2000, 3)), rng.uniform(0.01, 0.2, 2000)),
+        "mixed": (np.vstack([rng.uniform(-20, 20, (60, 3)), [[1e3, 1e3, 1e3]], [[np.nan, 0.0, 0.0]]]),
+                  np.concatenate([rng.uniform(0.5, 3.0, 60), [1.0], [1.0]])),
+    }
+    for name, (c, r) in sets.items():
+        c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
+        S = SphereSet(ctx, c, r)
+        sph, ns = oracle.make_spheres(c, r)
+        for fma in (0, 1):
+            got = edge_check_batch(t2, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_FMA_DOT if fma else 0)
+            want = _orc_edges(sph, ns, pts2, src, dst, W.ROBOT_RADIUS, fma)
+            assert np.array_equal(got, want), (name, fma, int((got != want).sum()))
+        assert got[:len(got) - 4:97].all()
+        if name in ("c3", "tiny"):
+            assert 0 < got.sum() < len(got)
