@@ -140,7 +140,7 @@ edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restric
   out[e] = hit ? 1 : 0;
 }
 
-// Warp-queue form of the same check (collide_queue.cuh): FP32 reject per lane, exact tests 32 at a time.
+// Item source of the two-stage form of the same check (collide_queue.cuh).
 template <bool SRC_TREE>
 struct BatchEdgeSrc {
   const double4 *pos;
@@ -164,19 +164,6 @@ struct BatchEdgeSrc {
   __device__ __forceinline__ bool accept(int, const double4 &, const double *, int) const { return true; }
   __device__ __forceinline__ void mark(int64_t i) const { out[i] = 1; }
 };
-
-template <bool FMA_DOT, bool SRC_TREE>
-__global__ void __launch_bounds__(256)
-edge_check_queue_kernel(BatchEdgeSrc<SRC_TREE> S, int64_t n_edges, const double4 *__restrict__ rec,
-                        const double2 *__restrict__ thr, const float4 *__restrict__ frec,
-                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ cov_start,
-                        const int32_t *__restrict__ cov_list, const SphGrid *__restrict__ Gp) {
-  __shared__ SphGrid G;
-  __shared__ int2 queue[8][CQ_CAP];
-  if (threadIdx.x == 0) G = *Gp;
-  __syncthreads();
-  cq_run<FMA_DOT>(S, n_edges, G, rec, thr, frec, cstart, cov_start, cov_list, queue[threadIdx.x >> 5]);
-}
 
 constexpr int SPH_TILE = 512;
 
@@ -258,20 +245,19 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
       b.cstart.ensure(SG_MAX_CELLS + 4, st);
       b.grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)b.grid.p;
-      const bool use_queue = n_edges >= cover_min_items();
+      const bool use_queue = n_edges >= cover_min_items() && n_edges < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, use_queue ? 1 : 0);
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);
-        build_sphere_cover(ctx, cv, b.rec2.p, b.thr2.p, b.cstart.p, dG, (int)spheres->n);
-        const unsigned qblocks = (unsigned)div_up(div_up(n_edges, (int64_t)32 * CQ_BATCHES), (int64_t)(TB / 32));
+        build_sphere_cover(ctx, cv, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, (int)spheres->n);
         if (from_tree) {
           BatchEdgeSrc<true> S{pos, dsrc, ddst, nullptr, nullptr, dout};
-          if (fma) edge_check_queue_kernel<true, true><<<qblocks, TB, 0, st>>>(S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, cv.start.p, cv.list.p, dG);
-          else     edge_check_queue_kernel<false, true><<<qblocks, TB, 0, st>>>(S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, cv.start.p, cv.list.p, dG);
+          if (fma) pq_launch<true>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
+          else     pq_launch<false>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
         } else {
           BatchEdgeSrc<false> S{nullptr, nullptr, nullptr, dstarts, dends, dout};
-          if (fma) edge_check_queue_kernel<true, false><<<qblocks, TB, 0, st>>>(S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, cv.start.p, cv.list.p, dG);
-          else     edge_check_queue_kernel<false, false><<<qblocks, TB, 0, st>>>(S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, cv.start.p, cv.list.p, dG);
+          if (fma) pq_launch<true>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
+          else     pq_launch<false>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
         }
       } else
       if (from_tree) {

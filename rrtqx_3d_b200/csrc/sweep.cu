@@ -368,7 +368,7 @@ add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const in
   }
 }
 
-// The same sweep in warp-queue form (collide_queue.cuh): items are the out-edges followed by one parent edge
+// The same sweep in two-stage form (collide_queue.cuh): items are the out-edges followed by one parent edge
 // per node; a colliding (edge, obstacle) pair counts only if the edge's start node passes the obstacle's
 // start-node filter.
 struct SweepEdgeSrc {
@@ -403,19 +403,6 @@ struct SweepEdgeSrc {
     if (i >= n_edges) node_flag[i - n_edges] = 1; else edge_flag[i] = 1;
   }
 };
-
-template <bool FMA_DOT>
-__global__ void __launch_bounds__(256)
-add_sweep_queue_kernel(SweepEdgeSrc S, int64_t n_items, const double4 *__restrict__ rec, const double2 *__restrict__ thr,
-                       const float4 *__restrict__ frec, const int32_t *__restrict__ cstart,
-                       const int32_t *__restrict__ cov_start, const int32_t *__restrict__ cov_list,
-                       const SphGrid *__restrict__ Gp) {
-  __shared__ SphGrid G;
-  __shared__ int2 queue[8][CQ_CAP];
-  if (threadIdx.x == 0) G = *Gp;
-  __syncthreads();
-  cq_run<FMA_DOT>(S, n_items, G, rec, thr, frec, cstart, cov_start, cov_list, queue[threadIdx.x >> 5]);
-}
 
 // removeObstacle: one thread per edge (upload order).  ob = table entry 0,
 // others = entries 1..n_tab-1 (thr / thr_le only).
@@ -549,19 +536,16 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       SphGrid *dG = (SphGrid *)R->grid.p;
       R->ob_frec2.ensure((size_t)n_obs + 1, st);
       const int64_t work = E->n_edges + E->n_nodes;
-      const bool use_queue = work >= cover_min_items();
+      const bool use_queue = work >= cover_min_items() && work < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
                                              R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, use_queue ? 1 : 0);
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);
-        build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->cstart.p, dG, (int)n_obs);
+        build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG, (int)n_obs);
         SweepEdgeSrc Q{E->tree->pos.p, E->n_edges, E->src.p, E->dst.p, par, R->ob_ext2.p, R->edge_flag.p, R->node_flag.p};
-        const unsigned qblocks = (unsigned)div_up(div_up(work, (int64_t)32 * CQ_BATCHES), (int64_t)(TB / 32));
-        if (flags & RRTQX_CHECK_FMA_DOT)
-          add_sweep_queue_kernel<true><<<qblocks, TB, 0, st>>>(Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, cv.start.p, cv.list.p, dG);
-        else
-          add_sweep_queue_kernel<false><<<qblocks, TB, 0, st>>>(Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, cv.start.p, cv.list.p, dG);
+        if (flags & RRTQX_CHECK_FMA_DOT) pq_launch<true>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
+        else                             pq_launch<false>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
       } else if (flags & RRTQX_CHECK_FMA_DOT)
         add_sweep_edge_kernel<true><<<div_up(work, TB), TB, 0, st>>>(E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par,
                                                                      R->ob_rec2.p, R->ob_thr2.p, R->ob_ext2.p, R->ob_frec2.p, R->cstart.p, dG,

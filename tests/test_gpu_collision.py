@@ -327,8 +327,8 @@ def test_edge_check_cover_lists_short_edges(ctx):
     t, src, dst, _ = _neighbour_graph(ctx, pts, 1.3)
     assert len(src) > 100000
     src, dst = src.copy(), dst.copy()
-    dst[::97] = src[::97]                                    # zero-length edges
     dst[5::101] = (src[5::101] + 7777) % len(pts)            # long edges (coarse rows)
+    dst[::97] = src[::97]                                    # zero-length edges
     far = np.array([[1e3, 1e3, 1e3], [1e3 + 0.2, 1e3, 1e3 + 0.1], [-500.0, 3.0, 2.0], [-500.1, 3.2, 2.0]])
     n0 = len(pts)
     pts2 = np.ascontiguousarray(np.vstack([pts, far]))       # short edges far outside the obstacle box
