@@ -653,15 +653,18 @@ def main():
                                   "colliding_edges": int(dflag.sum().item()),
                                   "algorithmic_bytes": len(src) * 9 + args.nodes * 32,
                                   "hbm_frac": (len(src) * 9 + args.nodes * 32) / (ems / 1e3) / 1e9 / peak_gbs}
-            # FP64 side of the bound (report max(B/BW, F/FP64)): one exact segment-sphere test is 39
-            # separately rounded FP64 operations (3 sub, 3 mul + 3 add dot, 1 div, 3 mul + 3 add closest point,
-            # 3 sub + 3 mul + 2 add radicand, 12 for the conservative reject; min/max/compare not counted); the
-            # unfused operations issue at one per lane per clock, i.e. half the measured FMA flop rate
-            fp64_tflops = ctx.measure_fp64_peak()
+            # FP64 side of the bound (report max(B/BW, F/FP64)).  The reference evaluates `pair_checks`
+            # (edge, obstacle) pairs (those that pass its start-node filter), 27 separately rounded FP64 operations
+            # each (3 sub, 3 mul + 3 add dot, 1 div, 3 mul + 3 add closest point, 3 sub + 3 mul + 2 add radicand) +
+            # 12 for a conservative FP64 reject = 39; the statistics kernel executes exactly that, and its fraction of
+            # the unfused FP64 rate (half the measured FMA flop rate) is reported.  The default two-stage path culls
+            # in FP32 on cover lists and runs the exact test only on the surviving pairs, so for it the reference-
+            # equivalent pair rate is the meaningful figure, not an FP64 utilisation.
             ops = n_tests * 39.0
             line["fp64_peak_tflops_measured"] = fp64_tflops
             line["edge_sweep"] = {"workload": "C3 obstacle-add sweep: 256 spheres vs all out-edges + parent edges of the 1M-node tree",
-                                  "fp64_ops_lower_bound": ops, "fp64_frac_of_unfused_peak": ops / (sms / 1e3) / (fp64_tflops / 2 * 1e12),
+                                  "fp64_ops_statistics_kernel": ops,
+                                  "fp64_frac_of_unfused_peak_statistics_kernel": ops / (float(np.mean(times_stats)) / 1e3) / (fp64_tflops / 2 * 1e12),
                                   "edges": n_e, "obstacles": args.sweep_obstacles, "pair_checks": n_tests,
                                   "candidate_nodes": n_cand, "blocked_edges": n_eh, "orphans": n_nh, "ms": sms,
                                   "ms_with_statistics_kernel": float(np.mean(times_stats)),

@@ -33,8 +33,8 @@ struct SphCoverBufs {
   DevBuf<int32_t> cnt, start, list, scan_tmp;
   DevBuf<float4> list_f;                // FP32 reject record of each list entry (saves one dependent load)
   DevBuf<uint2> pairs;                  // (item, obstacle) pairs that survived the reject
-  DevBuf<unsigned> slow;                // items decided by the slow kernel
-  DevBuf<unsigned long long> n_pairs;   // [0] pairs, [1] slow items
+  DevBuf<unsigned> slow;                // items decided by the slow kernels (list A, then list B)
+  DevBuf<unsigned long long> n_pairs;   // [0] pairs, [1] slow list A, [2] slow list B
 };
 
 // One warp per binned obstacle; FILL = false counts the cells it belongs to, FILL = true writes the lists.
@@ -118,7 +118,8 @@ static inline int64_t cover_min_items() {
 
 // ---------------------------------------------------------------- pair queue
 constexpr int PQ_THREADS = 128;  // collect kernel block
-constexpr int PQ_KEEP = 2;       // pairs an item may put on the list; items with more go to the slow list
+constexpr int PQ_KEEP = 4;       // pairs an item may put on the list; items with more go to the slow list
+constexpr unsigned PQ_NONE = 0xffffffffu;  // filler pair (skipped by the test kernel)
 
 // Src supplies the items:
 //   bool endpoints(int64_t i, double a[3], double b[3], int &v)   false: item has no edge (node without parent)
@@ -127,57 +128,67 @@ constexpr int PQ_KEEP = 2;       // pairs an item may put on the list; items wit
 //   void mark(int64_t i)                                            some accepted obstacle collides with item i
 //
 // Stage 1: one thread per item.  Candidates that survive the FP32 reject are kept in registers (at most
-// PQ_KEEP); at the end the thread publishes them as pairs through the block queue, or -- degenerate edge
-// (no reject possible, the reference collides it with every active obstacle) or more than PQ_KEEP survivors
-// -- puts the ITEM on the slow list.  No exact arithmetic here, so the kernel stays small; the lists cannot
-// overflow (<= PQ_KEEP pairs and <= 1 slow entry per item).
+// PQ_KEEP); at the end the thread publishes them as pairs through the block queue, or puts the ITEM on a slow
+// list: list B (one warp per item) for degenerate edges (no reject possible, the reference collides them
+// with every active obstacle) and long edges with more than PQ_KEEP survivors, list A (one thread per item)
+// for short edges with more than PQ_KEEP survivors.  No exact arithmetic here, so the kernel stays small.
+// The pair list holds `cap` pairs (2 per item); a block whose pairs do not fit any more turns its items into
+// list A entries, so nothing is lost (each item is on at most one slow list, once).
 template <class Src>
 __global__ void __launch_bounds__(PQ_THREADS)
 pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const int32_t *__restrict__ cstart,
                   const int32_t *__restrict__ cov_start, const int32_t *__restrict__ cov_list,
                   const float4 *__restrict__ cov_frec, const SphGrid *__restrict__ Gp, uint2 *__restrict__ pairs,
-                  unsigned *__restrict__ slow, unsigned long long *__restrict__ counters /* [0] pairs, [1] slow items */) {
-  __shared__ SphGrid G;
+                  unsigned long long cap, unsigned *__restrict__ slow_a, unsigned *__restrict__ slow_b,
+                  unsigned long long *__restrict__ counters /* [0] pairs, [1] list A, [2] list B */) {
+  const SphGrid &G = *Gp;  // uniform read-only loads
   __shared__ uint2 q[PQ_THREADS * PQ_KEEP];
+  __shared__ int keep[PQ_KEEP][PQ_THREADS];  // surviving candidates of each thread
   __shared__ unsigned sq[PQ_THREADS];
-  __shared__ unsigned qn, sn;
-  __shared__ unsigned long long qbase, sbase;
-  if (threadIdx.x == 0) { G = *Gp; qn = 0; sn = 0; }
-  __syncthreads();
+  __shared__ unsigned qn, sna, snb;
+  __shared__ unsigned long long qbase, sbase_a, sbase_b;
+  if (threadIdx.x == 0) { qn = 0; sna = 0; snb = 0; }
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int nk = 0;
-  int keep[PQ_KEEP];
-#pragma unroll
-  for (int k = 0; k < PQ_KEEP; ++k) keep[k] = 0;
-  bool to_slow = false;
+  bool to_slow = false, heavy = false;
   {
     double a[3], b[3];
     int v;
     if (i < n_items && S.endpoints(i, a, b, v)) {
       S.clear(i);
-      const SegPre pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
-      if (!pre.cullable) {
-        to_slow = true;
+      // the invariants this stage needs, without the FP64 sqrt: squared length, midpoint, and an FP32 upper
+      // bound of the half length.  s is the reference's radicand (same operations as seg_prepare), so
+      // s == 0 / non-finite is exactly len == 0 / non-finite.
+      const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
+      const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      const double mx = 0.5 * (a[0] + b[0]), my = 0.5 * (a[1] + b[1]), mz = 0.5 * (a[2] + b[2]);
+      if (!(s2 > 0.0) || !isfinite(s2) || !isfinite(mx + my + mz)) {
+        to_slow = heavy = true;  // degenerate (or undecidable here): the slow kernel works it out exactly
       } else {
-        const SegF32 sf = seg_f32(pre, G.cmax);
+        SegF32 sf;
+        sf.mx = __double2float_rn(mx); sf.my = __double2float_rn(my); sf.mz = __double2float_rn(mz);
+        float rt;  // sqrt.approx: 1 ulp-level error, covered by the 1e-6 factor; + 1e-19 for flushed subnormals
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(__double2float_ru(s2)));
+        sf.half = 0.5f * (rt * 1.000001f) + 1e-19f;  // >= len / 2
+        sf.bound = 3.0e-7f * (G.cmax + fmaxf(fabsf(sf.mx), fmaxf(fabsf(sf.my), fabsf(sf.mz))));
+        sf.ok = isfinite(sf.bound) && isfinite(sf.half);
+        heavy = !(G.cov_on && s2 <= G.cov_len2);
         auto visit = [&](int o, const float4 f) {
           if (seg_reject_f32(sf, f)) return;
-#pragma unroll
-          for (int k = 0; k < PQ_KEEP; ++k)
-            if (nk == k) keep[k] = o;
+          if (nk < PQ_KEEP) keep[nk][threadIdx.x] = o;
           ++nk;
         };
         const int ncell = G.nx * G.ny * G.nz;
-        if (G.cov_on && pre.half <= G.cov_cap) {
-          const int c = (sg_cell(pre.mz, G.clo[2], G.cinv[2], COV_DIM) * COV_DIM + sg_cell(pre.my, G.clo[1], G.cinv[1], COV_DIM)) * COV_DIM +
-                        sg_cell(pre.mx, G.clo[0], G.cinv[0], COV_DIM);
+        if (!heavy) {
+          const int c = (sg_cell(mz, G.clo[2], G.cinv[2], COV_DIM) * COV_DIM + sg_cell(my, G.clo[1], G.cinv[1], COV_DIM)) * COV_DIM +
+                        sg_cell(mx, G.clo[0], G.cinv[0], COV_DIM);
           const int k1 = cov_start[c + 1];
           for (int k = cov_start[c]; k < k1; ++k) visit(cov_list[k], cov_frec[k]);
         } else {
-          const double R = (pre.half + G.thr_max) * (1.0 + 1e-9) + 1e-300;
-          const int x0 = sg_cell(pre.mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(pre.mx + R, G.lo[0], G.inv[0], G.nx);
-          const int y0 = sg_cell(pre.my - R, G.lo[1], G.inv[1], G.ny), y1 = sg_cell(pre.my + R, G.lo[1], G.inv[1], G.ny);
-          const int z0 = sg_cell(pre.mz - R, G.lo[2], G.inv[2], G.nz), z1 = sg_cell(pre.mz + R, G.lo[2], G.inv[2], G.nz);
+          const double R = (0.5 * __dsqrt_ru(s2) + G.thr_max) * (1.0 + 1e-9) + 1e-300;
+          const int x0 = sg_cell(mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(mx + R, G.lo[0], G.inv[0], G.nx);
+          const int y0 = sg_cell(my - R, G.lo[1], G.inv[1], G.ny), y1 = sg_cell(my + R, G.lo[1], G.inv[1], G.ny);
+          const int z0 = sg_cell(mz - R, G.lo[2], G.inv[2], G.nz), z1 = sg_cell(mz + R, G.lo[2], G.inv[2], G.nz);
           for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y) {
               const int cb = (z * G.ny + y) * G.nx;
@@ -191,32 +202,41 @@ pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const
       }
     }
   }
-  if (to_slow) {
-    sq[atomicAdd(&sn, 1u)] = (unsigned)i;
+  __syncthreads();  // qn, sna, snb initialised
+  if (to_slow) {  // list A from the front of sq, list B from its back
+    if (heavy) sq[PQ_THREADS - 1 - atomicAdd(&snb, 1u)] = (unsigned)i;
+    else       sq[atomicAdd(&sna, 1u)] = (unsigned)i;
   } else if (nk) {
     const unsigned k0 = atomicAdd(&qn, (unsigned)nk);
-#pragma unroll
-    for (int k = 0; k < PQ_KEEP; ++k)
-      if (k < nk) q[k0 + k] = make_uint2((unsigned)i, (unsigned)keep[k]);
+    for (int k = 0; k < nk; ++k) q[k0 + k] = make_uint2((unsigned)i, (unsigned)keep[k][threadIdx.x]);
   }
   __syncthreads();
-  const unsigned n = qn, ns = sn;
+  const unsigned n = qn, na = sna, nb = snb;
   if (threadIdx.x == 0 && n) qbase = atomicAdd(&counters[0], (unsigned long long)n);
-  if (threadIdx.x == 32 && ns) sbase = atomicAdd(&counters[1], (unsigned long long)ns);
+  if (threadIdx.x == 32 && na) sbase_a = atomicAdd(&counters[1], (unsigned long long)na);
+  if (threadIdx.x == 64 && nb) sbase_b = atomicAdd(&counters[2], (unsigned long long)nb);
   __syncthreads();
-  for (unsigned k = threadIdx.x; k < n; k += blockDim.x) pairs[qbase + k] = q[k];
-  if (threadIdx.x < ns) slow[sbase + threadIdx.x] = sq[threadIdx.x];
+  if (n && qbase + n > cap) {  // pair list full: fillers into what is left of it, the items go to list A
+    for (unsigned k = threadIdx.x; k < n; k += blockDim.x)
+      if (qbase + k < cap) pairs[qbase + k] = make_uint2(PQ_NONE, 0u);
+    if (nk && !to_slow) slow_a[atomicAdd(&counters[1], 1ull)] = (unsigned)i;
+  } else {
+    for (unsigned k = threadIdx.x; k < n; k += blockDim.x) pairs[qbase + k] = q[k];
+  }
+  if (threadIdx.x < na) slow_a[sbase_a + threadIdx.x] = sq[threadIdx.x];
+  if (threadIdx.x < nb) slow_b[sbase_b + threadIdx.x] = sq[PQ_THREADS - 1 - threadIdx.x];
 }
 
 // Stage 2: one thread per pair, exact test (edge invariants recomputed from the endpoints).
 template <bool FMA_DOT, class Src>
 __global__ void __launch_bounds__(256)
 pq_test_kernel(Src S, const double4 *__restrict__ rec, const double2 *__restrict__ thr, const uint2 *__restrict__ pairs,
-               const unsigned long long *__restrict__ counters) {
-  const unsigned long long n = counters[0];
+               unsigned long long cap, const unsigned long long *__restrict__ counters) {
+  const unsigned long long n = min(counters[0], cap);
   for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
        p += (unsigned long long)gridDim.x * blockDim.x) {
     const uint2 e = pairs[p];
+    if (e.x == PQ_NONE) continue;
     double a[3], b[3];
     int v;
     S.endpoints((int64_t)e.x, a, b, v);
@@ -226,31 +246,38 @@ pq_test_kernel(Src S, const double4 *__restrict__ rec, const double2 *__restrict
   }
 }
 
-// Slow items: one thread per item, every candidate decided in place, first hit ends it (the shape of the
-// thread-per-edge kernels; few items get here).
-template <bool FMA_DOT, class Src>
+// Slow items, every candidate decided in place, the item ends at the first hit.  WARP = false: one thread per
+// item (list A: short edges with many surviving candidates).  WARP = true: one warp per item, the candidates of
+// a row spread over the lanes (list B: degenerate and long edges, which may meet most of the table).
+template <bool FMA_DOT, bool WARP, class Src>
 __global__ void __launch_bounds__(128)
 pq_slow_kernel(Src S, const double4 *__restrict__ rec, const double2 *__restrict__ thr, const float4 *__restrict__ frec,
                const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, const unsigned *__restrict__ slow,
-               const unsigned long long *__restrict__ counters) {
+               const unsigned long long *__restrict__ count) {
   __shared__ SphGrid G;
   if (threadIdx.x == 0) G = *Gp;
   __syncthreads();
-  const unsigned long long n = counters[1];
-  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
-       p += (unsigned long long)gridDim.x * blockDim.x) {
+  const int lane = WARP ? (threadIdx.x & 31) : 0, step = WARP ? 32 : 1;
+  const unsigned long long n = *count;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long p = WARP ? tid >> 5 : tid; p < n; p += WARP ? nthr >> 5 : nthr) {
     const int64_t i = (int64_t)slow[p];
     double a[3], b[3];
     int v;
     S.endpoints(i, a, b, v);
     const SegPre pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
     const SegF32 sf = seg_f32(pre, G.cmax);
-    bool hit = false;
+    bool hit = false;  // warp-uniform when WARP
     auto run = [&](int lo, int hi) {
-      for (int o = lo; o < hi && !hit; ++o) {
-        if (seg_reject_f32(sf, frec[o])) continue;  // never rejects a degenerate edge (sf.ok false)
-        const double4 r = rec[o];
-        hit = seg_sphere_collide_exact<FMA_DOT>(pre, r.x, r.y, r.z, thr[o].y) && S.accept(o, r, a, v);
+      for (int o0 = lo; o0 < hi && !hit; o0 += step) {
+        const int o = o0 + lane;
+        bool h = false;
+        if (o < hi && !seg_reject_f32(sf, frec[o])) {  // never rejects a degenerate edge (sf.ok false)
+          const double4 r = rec[o];
+          h = seg_sphere_collide_exact<FMA_DOT>(pre, r.x, r.y, r.z, thr[o].y) && S.accept(o, r, a, v);
+        }
+        hit = WARP ? __any_sync(FULL, h) : h;
       }
     };
     const int ncell = G.nx * G.ny * G.nz;
@@ -268,26 +295,30 @@ pq_slow_kernel(Src S, const double4 *__restrict__ rec, const double2 *__restrict
         }
       if (!hit) run(cstart[ncell], cstart[ncell + 1]);
     }
-    if (hit) S.mark(i);
+    if (hit && lane == 0) S.mark(i);
   }
 }
 
-// The three kernels on the context's stream.  Requires n_items < 2^32 (32-bit item numbers in the lists).
+// The four kernels on the context's stream.  Requires n_items < 2^32 (32-bit item numbers in the lists).
 template <bool FMA_DOT, class Src>
 static inline void pq_launch(rrtqx_ctx *ctx, SphCoverBufs &B, const Src &S, int64_t n_items, const double4 *rec,
                              const double2 *thr, const float4 *frec, const int32_t *cstart, const SphGrid *dG) {
   cudaStream_t st = ctx->stream;
-  B.pairs.ensure((size_t)n_items * PQ_KEEP + 1, st);
-  B.slow.ensure((size_t)n_items + 1, st);
-  B.n_pairs.ensure(2, st);
-  RQ_CUDA(cudaMemsetAsync(B.n_pairs.p, 0, 2 * sizeof(unsigned long long), st));
+  const unsigned long long cap = 2ull * (unsigned long long)n_items + 1024;
+  B.pairs.ensure((size_t)cap, st);
+  B.slow.ensure(2 * (size_t)n_items + 2, st);
+  B.n_pairs.ensure(4, st);
+  unsigned *slow_a = B.slow.p, *slow_b = B.slow.p + n_items + 1;
+  RQ_CUDA(cudaMemsetAsync(B.n_pairs.p, 0, 4 * sizeof(unsigned long long), st));
   pq_collect_kernel<Src><<<(unsigned)div_up(n_items, (int64_t)PQ_THREADS), PQ_THREADS, 0, st>>>(S, n_items, frec, cstart, B.start.p, B.list.p,
-                                                                                                  B.list_f.p, dG, B.pairs.p, B.slow.p, B.n_pairs.p);
-  const unsigned tblocks = (unsigned)std::min<int64_t>(div_up(n_items * PQ_KEEP, (int64_t)256), (int64_t)ctx->sm_count * 8);
-  pq_test_kernel<FMA_DOT, Src><<<tblocks, 256, 0, st>>>(S, rec, thr, B.pairs.p, B.n_pairs.p);
-  const unsigned sblocks = (unsigned)std::min<int64_t>(div_up(n_items, (int64_t)128), (int64_t)ctx->sm_count * 4);
-  pq_slow_kernel<FMA_DOT, Src><<<sblocks, 128, 0, st>>>(S, rec, thr, frec, cstart, dG, B.slow.p, B.n_pairs.p);
-  post_launch(ctx, 3);
+                                                                                                  B.list_f.p, dG, B.pairs.p, cap, slow_a, slow_b, B.n_pairs.p);
+  const unsigned tblocks = (unsigned)std::min<int64_t>(div_up((int64_t)cap, (int64_t)256), (int64_t)ctx->sm_count * 8);
+  pq_test_kernel<FMA_DOT, Src><<<tblocks, 256, 0, st>>>(S, rec, thr, B.pairs.p, cap, B.n_pairs.p);
+  const unsigned ablocks = (unsigned)std::min<int64_t>(div_up(n_items, (int64_t)128), (int64_t)ctx->sm_count * 4);
+  pq_slow_kernel<FMA_DOT, false, Src><<<ablocks, 128, 0, st>>>(S, rec, thr, frec, cstart, dG, slow_a, B.n_pairs.p + 1);
+  const unsigned bblocks = (unsigned)std::min<int64_t>(div_up(n_items, (int64_t)4), (int64_t)ctx->sm_count * 8);
+  pq_slow_kernel<FMA_DOT, true, Src><<<bblocks, 128, 0, st>>>(S, rec, thr, frec, cstart, dG, slow_b, B.n_pairs.p + 2);
+  post_launch(ctx, 4);
 }
 
 #endif  // __CUDACC__

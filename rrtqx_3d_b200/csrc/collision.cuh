@@ -135,6 +135,7 @@ struct SphGrid {
   int cnx, cny, cnz;
   double clo[3], cinv[3], ccell[3];
   double cov_cap, cov_margin;
+  double cov_len2;  // an edge with squared length <= cov_len2 has half length <= cov_cap
 };
 constexpr int SG_MAX_DIM = 16;
 constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
@@ -143,9 +144,8 @@ constexpr int COV_CELLS = COV_DIM * COV_DIM * COV_DIM;
 constexpr int COV_BUDGET = 1 << 20;  // entries of all cover lists together; above it the cover is switched off
 
 __device__ __forceinline__ int sg_cell(double v, double lo, double inv, int n) {
-  double c = floor((v - lo) * inv);
-  c = fmin(fmax(c, 0.0), (double)(n - 1));  // NaN -> 0
-  return (int)c;
+  const int c = __double2int_rd((v - lo) * inv);  // floor, saturating; NaN -> 0
+  return min(max(c, 0), n - 1);
 }
 
 static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const double2 *__restrict__ thr,
@@ -211,6 +211,7 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
     g.cnx = g.cny = g.cnz = 1;
     g.cov_cap = 0.0;
     g.cov_margin = 0.0;
+    g.cov_len2 = -1.0;
     double cap = INFINITY, span = 0.0;
     bool ok = g.thr_max > 0.0;
     for (int c = 0; c < 3; ++c) {
@@ -229,6 +230,7 @@ static __global__ void sphere_grid_kernel(const double4 *__restrict__ rec, const
       g.cnx = g.cny = g.cnz = COV_DIM;
       g.cov_cap = cap;
       g.cov_margin = 1e-9 * (r7[7] + span + g.thr_max);
+      g.cov_len2 = 4.0 * cap * cap * (1.0 - 1e-9);
     }
     *G = g;
   }
