@@ -660,6 +660,7 @@ def main():
             # the unfused FP64 rate (half the measured FMA flop rate) is reported.  The default two-stage path culls
             # in FP32 on cover lists and runs the exact test only on the surviving pairs, so for it the reference-
             # equivalent pair rate is the meaningful figure, not an FP64 utilisation.
+            fp64_tflops = ctx.measure_fp64_peak()
             ops = n_tests * 39.0
             line["fp64_peak_tflops_measured"] = fp64_tflops
             line["edge_sweep"] = {"workload": "C3 obstacle-add sweep: 256 spheres vs all out-edges + parent edges of the 1M-node tree",
