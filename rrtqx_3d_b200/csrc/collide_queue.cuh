@@ -20,7 +20,6 @@
 // fall back to the coarse rows.
 #pragma once
 #include "collision.cuh"
-#include "scan.cuh"
 #include <cstdlib>
 #include <map>
 
@@ -29,27 +28,30 @@ namespace rrtqx {
 #ifdef __CUDACC__
 
 // ---------------------------------------------------------------- cover lists
+constexpr int COV_CAPC = 32;  // entries per cover cell; a fuller cell switches the cover off (coarse rows instead)
+
 struct SphCoverBufs {
-  DevBuf<int32_t> cnt, start, list, scan_tmp;
-  DevBuf<float4> list_f;                // FP32 reject record of each list entry (saves one dependent load)
+  DevBuf<int32_t> cnt;                  // entries of each cover cell
+  DevBuf<int32_t> list;                 // COV_CAPC obstacle numbers per cell
+  DevBuf<float4> list_f;                // their FP32 reject records (saves one dependent load)
   DevBuf<uint2> pairs;                  // (item, obstacle) pairs that survived the reject
   DevBuf<unsigned> slow;                // items decided by the slow kernels (list A, then list B)
   DevBuf<unsigned long long> n_pairs;   // [0] pairs, [1] slow list A, [2] slow list B
 };
 
-// One warp per binned obstacle; FILL = false counts the cells it belongs to, FILL = true writes the lists.
-template <bool FILL>
-__global__ void __launch_bounds__(256)
-cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restrict__ thr2, const int32_t *__restrict__ cstart,
-                      const SphGrid *__restrict__ Gp, int n_upper, int32_t *__restrict__ cnt,
-                      const int32_t *__restrict__ start, int32_t *__restrict__ list, const float4 *__restrict__ frec2,
-                      float4 *__restrict__ list_f) {
+// One warp per binned obstacle: append it to every cover cell it belongs to (fixed-capacity lists, so one pass,
+// no scan).  cnt[] must be zero.
+static __global__ void __launch_bounds__(256)
+cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restrict__ thr2, const float4 *__restrict__ frec2,
+                      const int32_t *__restrict__ cstart, SphGrid *__restrict__ Gp, int n_upper, int32_t *__restrict__ cnt,
+                      int32_t *__restrict__ list, float4 *__restrict__ list_f) {
   const int o = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (o >= n_upper) return;
   const SphGrid &G = *Gp;
   if (!G.cov_on) return;
   if (o >= cstart[G.nx * G.ny * G.nz]) return;  // the non-finite ones stay in the "always" bucket
   const double4 r = rec2[o];
+  const float4 fr = frec2[o];
   const double c[3] = {r.x, r.y, r.z};
   const double rho = (thr2[o].x + G.cov_cap) * (1.0 + 1e-9) + G.cov_margin;
   int a[3], n[3];
@@ -70,16 +72,14 @@ cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restric
     if (d2 <= rho * rho) {
       const int cell = (i[2] * COV_DIM + i[1]) * COV_DIM + i[0];
       const int p = atomicAdd(&cnt[cell], 1);
-      if (FILL) {
-        list[start[cell] + p] = o;
-        list_f[start[cell] + p] = frec2[o];
+      if (p < COV_CAPC) {
+        list[cell * COV_CAPC + p] = o;
+        list_f[cell * COV_CAPC + p] = fr;
+      } else {
+        Gp->cov_on = 0;  // too dense for the cover: every consumer falls back to the coarse rows
       }
     }
   }
-}
-
-static __global__ void cover_finalize_kernel(SphGrid *G, const int32_t *__restrict__ start) {
-  if (start[COV_CELLS] > COV_BUDGET) G->cov_on = 0;
 }
 
 // After sphere_grid_kernel(..., cover = 1) on the same stream.  n_upper: upper bound of the table size.
@@ -87,17 +87,12 @@ static inline void build_sphere_cover(rrtqx_ctx *ctx, SphCoverBufs &B, const dou
                                       const float4 *frec2, const int32_t *cstart, SphGrid *dG, int n_upper) {
   cudaStream_t st = ctx->stream;
   B.cnt.ensure(COV_CELLS + 1, st);
-  B.start.ensure(COV_CELLS + 2, st);
-  B.list.ensure(COV_BUDGET, st);
-  B.list_f.ensure(COV_BUDGET, st);
+  B.list.ensure((size_t)COV_CELLS * COV_CAPC, st);
+  B.list_f.ensure((size_t)COV_CELLS * COV_CAPC, st);
   RQ_CUDA(cudaMemsetAsync(B.cnt.p, 0, (COV_CELLS + 1) * sizeof(int32_t), st));
   const unsigned blocks = (unsigned)div_up((int64_t)n_upper * 32, (int64_t)256);
-  cover_register_kernel<false><<<blocks, 256, 0, st>>>(rec2, thr2, cstart, dG, n_upper, B.cnt.p, nullptr, nullptr, nullptr, nullptr);
-  exclusive_scan<int32_t, int32_t>(ctx, B.cnt.p, COV_CELLS, B.start.p, B.scan_tmp);
-  cover_finalize_kernel<<<1, 1, 0, st>>>(dG, B.start.p);
-  RQ_CUDA(cudaMemsetAsync(B.cnt.p, 0, (COV_CELLS + 1) * sizeof(int32_t), st));
-  cover_register_kernel<true><<<blocks, 256, 0, st>>>(rec2, thr2, cstart, dG, n_upper, B.cnt.p, B.start.p, B.list.p, frec2, B.list_f.p);
-  post_launch(ctx, 3);
+  cover_register_kernel<<<blocks, 256, 0, st>>>(rec2, thr2, frec2, cstart, dG, n_upper, B.cnt.p, B.list.p, B.list_f.p);
+  post_launch(ctx, 1);
 }
 
 static inline SphCoverBufs &cover_bufs(rrtqx_ctx *ctx) {
@@ -137,7 +132,7 @@ constexpr unsigned PQ_NONE = 0xffffffffu;  // filler pair (skipped by the test k
 template <class Src>
 __global__ void __launch_bounds__(PQ_THREADS)
 pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const int32_t *__restrict__ cstart,
-                  const int32_t *__restrict__ cov_start, const int32_t *__restrict__ cov_list,
+                  const int32_t *__restrict__ cov_cnt, const int32_t *__restrict__ cov_list,
                   const float4 *__restrict__ cov_frec, const SphGrid *__restrict__ Gp, uint2 *__restrict__ pairs,
                   unsigned long long cap, unsigned *__restrict__ slow_a, unsigned *__restrict__ slow_b,
                   unsigned long long *__restrict__ counters /* [0] pairs, [1] list A, [2] list B */) {
@@ -182,8 +177,8 @@ pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const
         if (!heavy) {
           const int c = (sg_cell(mz, G.clo[2], G.cinv[2], COV_DIM) * COV_DIM + sg_cell(my, G.clo[1], G.cinv[1], COV_DIM)) * COV_DIM +
                         sg_cell(mx, G.clo[0], G.cinv[0], COV_DIM);
-          const int k1 = cov_start[c + 1];
-          for (int k = cov_start[c]; k < k1; ++k) visit(cov_list[k], cov_frec[k]);
+          const int k1 = c * COV_CAPC + cov_cnt[c];  // cov_on => no cell over capacity
+          for (int k = c * COV_CAPC; k < k1; ++k) visit(cov_list[k], cov_frec[k]);
         } else {
           const double R = (0.5 * __dsqrt_ru(s2) + G.thr_max) * (1.0 + 1e-9) + 1e-300;
           const int x0 = sg_cell(mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(mx + R, G.lo[0], G.inv[0], G.nx);
@@ -310,7 +305,7 @@ static inline void pq_launch(rrtqx_ctx *ctx, SphCoverBufs &B, const Src &S, int6
   B.n_pairs.ensure(4, st);
   unsigned *slow_a = B.slow.p, *slow_b = B.slow.p + n_items + 1;
   RQ_CUDA(cudaMemsetAsync(B.n_pairs.p, 0, 4 * sizeof(unsigned long long), st));
-  pq_collect_kernel<Src><<<(unsigned)div_up(n_items, (int64_t)PQ_THREADS), PQ_THREADS, 0, st>>>(S, n_items, frec, cstart, B.start.p, B.list.p,
+  pq_collect_kernel<Src><<<(unsigned)div_up(n_items, (int64_t)PQ_THREADS), PQ_THREADS, 0, st>>>(S, n_items, frec, cstart, B.cnt.p, B.list.p,
                                                                                                   B.list_f.p, dG, B.pairs.p, cap, slow_a, slow_b, B.n_pairs.p);
   const unsigned tblocks = (unsigned)std::min<int64_t>(div_up((int64_t)cap, (int64_t)256), (int64_t)ctx->sm_count * 8);
   pq_test_kernel<FMA_DOT, Src><<<tblocks, 256, 0, st>>>(S, rec, thr, B.pairs.p, cap, B.n_pairs.p);

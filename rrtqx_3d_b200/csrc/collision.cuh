@@ -141,7 +141,6 @@ constexpr int SG_MAX_DIM = 16;
 constexpr int SG_MAX_CELLS = SG_MAX_DIM * SG_MAX_DIM * SG_MAX_DIM;
 constexpr int COV_DIM = 32;
 constexpr int COV_CELLS = COV_DIM * COV_DIM * COV_DIM;
-constexpr int COV_BUDGET = 1 << 20;  // entries of all cover lists together; above it the cover is switched off
 
 __device__ __forceinline__ int sg_cell(double v, double lo, double inv, int n) {
   const int c = __double2int_rd((v - lo) * inv);  // floor, saturating; NaN -> 0
