@@ -16,8 +16,10 @@
 // they read the list of the one cover cell that holds their midpoint.  Obstacle o is on the list of cell c iff
 // dist(c_o, box(c)) <= thr_o + cov_cap (+ margin), which contains every obstacle with |c_o - mid| <= thr_o +
 // half for any midpoint in the cell; border cells extend to infinity, so midpoints outside the grid are
-// covered too.  C3: about 1 candidate per edge instead of 16.  Longer edges and over-budget obstacle sets
-// fall back to the coarse rows.
+// covered too.  C3: about 1.3 candidates per edge instead of 16.  Lists have a fixed capacity per cell (one
+// build pass, no scan; an entry is the 16-byte FP32 reject record with the obstacle number packed into it);
+// an obstacle set too dense for that, or with more than 65536 obstacles, switches the cover off and every
+// edge walks the coarse rows, as longer edges always do.
 #pragma once
 #include "collision.cuh"
 #include <cstdlib>
@@ -32,8 +34,8 @@ constexpr int COV_CAPC = 32;  // entries per cover cell; a fuller cell switches 
 
 struct SphCoverBufs {
   DevBuf<int32_t> cnt;                  // entries of each cover cell
-  DevBuf<int32_t> list;                 // COV_CAPC obstacle numbers per cell
-  DevBuf<float4> list_f;                // their FP32 reject records (saves one dependent load)
+  DevBuf<float4> list_f;                // COV_CAPC entries per cell: FP32 reject record with the obstacle number packed
+                                        // into the low 16 bits of .w (threshold rounded up to the upper 16 bits)
   DevBuf<uint2> pairs;                  // (item, obstacle) pairs that survived the reject
   DevBuf<unsigned> slow;                // items decided by the slow kernels (list A, then list B)
   DevBuf<unsigned long long> n_pairs;   // [0] pairs, [1] slow list A, [2] slow list B
@@ -44,14 +46,19 @@ struct SphCoverBufs {
 static __global__ void __launch_bounds__(256)
 cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restrict__ thr2, const float4 *__restrict__ frec2,
                       const int32_t *__restrict__ cstart, SphGrid *__restrict__ Gp, int n_upper, int32_t *__restrict__ cnt,
-                      int32_t *__restrict__ list, float4 *__restrict__ list_f) {
+                      float4 *__restrict__ list_f) {
   const int o = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (o >= n_upper) return;
   const SphGrid &G = *Gp;
   if (!G.cov_on) return;
   if (o >= cstart[G.nx * G.ny * G.nz]) return;  // the non-finite ones stay in the "always" bucket
   const double4 r = rec2[o];
-  const float4 fr = frec2[o];
+  float4 fr = frec2[o];
+  {  // .w = threshold, made coarser in the conservative direction (larger), + obstacle number (o < 65536)
+    const unsigned b = __float_as_uint(fr.w);
+    const unsigned up = (b >> 31) ? (b & 0xffff0000u) : ((b + 0xffffu) & 0xffff0000u);
+    fr.w = __uint_as_float(up | (unsigned)o);
+  }
   const double c[3] = {r.x, r.y, r.z};
   const double rho = (thr2[o].x + G.cov_cap) * (1.0 + 1e-9) + G.cov_margin;
   int a[3], n[3];
@@ -73,7 +80,6 @@ cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restric
       const int cell = (i[2] * COV_DIM + i[1]) * COV_DIM + i[0];
       const int p = atomicAdd(&cnt[cell], 1);
       if (p < COV_CAPC) {
-        list[cell * COV_CAPC + p] = o;
         list_f[cell * COV_CAPC + p] = fr;
       } else {
         Gp->cov_on = 0;  // too dense for the cover: every consumer falls back to the coarse rows
@@ -82,16 +88,18 @@ cover_register_kernel(const double4 *__restrict__ rec2, const double2 *__restric
   }
 }
 
-// After sphere_grid_kernel(..., cover = 1) on the same stream.  n_upper: upper bound of the table size.
+constexpr int COV_MAX_OBSTACLES = 65536;  // obstacle numbers are packed into 16 bits of the list entries
+
+// After sphere_grid_kernel(..., cover = 1) on the same stream.  n_upper: upper bound of the table size
+// (<= COV_MAX_OBSTACLES, else the caller asks sphere_grid_kernel for cover = 0 and skips this).
 static inline void build_sphere_cover(rrtqx_ctx *ctx, SphCoverBufs &B, const double4 *rec2, const double2 *thr2,
                                       const float4 *frec2, const int32_t *cstart, SphGrid *dG, int n_upper) {
   cudaStream_t st = ctx->stream;
   B.cnt.ensure(COV_CELLS + 1, st);
-  B.list.ensure((size_t)COV_CELLS * COV_CAPC, st);
   B.list_f.ensure((size_t)COV_CELLS * COV_CAPC, st);
   RQ_CUDA(cudaMemsetAsync(B.cnt.p, 0, (COV_CELLS + 1) * sizeof(int32_t), st));
   const unsigned blocks = (unsigned)div_up((int64_t)n_upper * 32, (int64_t)256);
-  cover_register_kernel<<<blocks, 256, 0, st>>>(rec2, thr2, frec2, cstart, dG, n_upper, B.cnt.p, B.list.p, B.list_f.p);
+  cover_register_kernel<<<blocks, 256, 0, st>>>(rec2, thr2, frec2, cstart, dG, n_upper, B.cnt.p, B.list_f.p);
   post_launch(ctx, 1);
 }
 
@@ -132,7 +140,7 @@ constexpr unsigned PQ_NONE = 0xffffffffu;  // filler pair (skipped by the test k
 template <class Src>
 __global__ void __launch_bounds__(PQ_THREADS)
 pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const int32_t *__restrict__ cstart,
-                  const int32_t *__restrict__ cov_cnt, const int32_t *__restrict__ cov_list,
+                  const int32_t *__restrict__ cov_cnt,
                   const float4 *__restrict__ cov_frec, const SphGrid *__restrict__ Gp, uint2 *__restrict__ pairs,
                   unsigned long long cap, unsigned *__restrict__ slow_a, unsigned *__restrict__ slow_b,
                   unsigned long long *__restrict__ counters /* [0] pairs, [1] list A, [2] list B */) {
@@ -178,7 +186,12 @@ pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const
           const int c = (sg_cell(mz, G.clo[2], G.cinv[2], COV_DIM) * COV_DIM + sg_cell(my, G.clo[1], G.cinv[1], COV_DIM)) * COV_DIM +
                         sg_cell(mx, G.clo[0], G.cinv[0], COV_DIM);
           const int k1 = c * COV_CAPC + cov_cnt[c];  // cov_on => no cell over capacity
-          for (int k = c * COV_CAPC; k < k1; ++k) visit(cov_list[k], cov_frec[k]);
+          for (int k = c * COV_CAPC; k < k1; ++k) {
+            float4 f = cov_frec[k];
+            const unsigned w = __float_as_uint(f.w);
+            f.w = __uint_as_float(w & 0xffff0000u);
+            visit((int)(w & 0xffffu), f);
+          }
         } else {
           const double R = (0.5 * __dsqrt_ru(s2) + G.thr_max) * (1.0 + 1e-9) + 1e-300;
           const int x0 = sg_cell(mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(mx + R, G.lo[0], G.inv[0], G.nx);
@@ -305,7 +318,7 @@ static inline void pq_launch(rrtqx_ctx *ctx, SphCoverBufs &B, const Src &S, int6
   B.n_pairs.ensure(4, st);
   unsigned *slow_a = B.slow.p, *slow_b = B.slow.p + n_items + 1;
   RQ_CUDA(cudaMemsetAsync(B.n_pairs.p, 0, 4 * sizeof(unsigned long long), st));
-  pq_collect_kernel<Src><<<(unsigned)div_up(n_items, (int64_t)PQ_THREADS), PQ_THREADS, 0, st>>>(S, n_items, frec, cstart, B.cnt.p, B.list.p,
+  pq_collect_kernel<Src><<<(unsigned)div_up(n_items, (int64_t)PQ_THREADS), PQ_THREADS, 0, st>>>(S, n_items, frec, cstart, B.cnt.p,
                                                                                                   B.list_f.p, dG, B.pairs.p, cap, slow_a, slow_b, B.n_pairs.p);
   const unsigned tblocks = (unsigned)std::min<int64_t>(div_up((int64_t)cap, (int64_t)256), (int64_t)ctx->sm_count * 8);
   pq_test_kernel<FMA_DOT, Src><<<tblocks, 256, 0, st>>>(S, rec, thr, B.pairs.p, cap, B.n_pairs.p);

@@ -538,11 +538,11 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       const int64_t work = E->n_edges + E->n_nodes;
       const bool use_queue = work >= cover_min_items() && work < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
-                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, use_queue ? 1 : 0);
+                                             R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, (use_queue && n_obs <= COV_MAX_OBSTACLES) ? 1 : 0);
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);
-        build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG, (int)n_obs);
+        if (n_obs <= COV_MAX_OBSTACLES) build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG, (int)n_obs);
         SweepEdgeSrc Q{E->tree->pos.p, E->n_edges, E->src.p, E->dst.p, par, R->ob_ext2.p, R->edge_flag.p, R->node_flag.p};
         if (flags & RRTQX_CHECK_FMA_DOT) pq_launch<true>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
         else                             pq_launch<false>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
