@@ -463,23 +463,52 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
 }
 
 // ------------------------------------------------------- flag compaction
-__global__ void compact_flags_kernel(const uint8_t *__restrict__ flag, const int32_t *__restrict__ scan, int64_t n,
-                                     int32_t *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) out[scan[i]] = (int32_t)i;
+// Ordered compaction of a byte-flag array into an id list without a per-element scan array: tile counts
+// (scan_tile_sums_kernel), a scan of the tile counts, then each block ranks its own tile of SCAN_TILE flags
+// (8 consecutive flags per thread) and writes the ids in ascending order.
+__global__ void __launch_bounds__(SCAN_THREADS)
+compact_tiles_kernel(const uint8_t *__restrict__ flag, int64_t n, const int32_t *__restrict__ tile_offsets,
+                     int32_t *__restrict__ out) {
+  __shared__ int32_t sm[33];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned char f[SCAN_ITEMS];
+  int32_t cnt = 0;
+  if (base + SCAN_ITEMS <= n) {  // flag arrays come from cudaMalloc and base is a multiple of 8
+    const uint2 w = *reinterpret_cast<const uint2 *>(flag + base);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[k] = (w.x >> (8 * k)) & 0xff; f[4 + k] = (w.y >> (8 * k)) & 0xff; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) f[k] = base + k < n ? flag[base + k] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) cnt += f[k] ? 1 : 0;
+  int32_t pos = block_exclusive_scan<int32_t>(cnt, sm, (int32_t *)nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (f[k]) out[pos++] = (int32_t)(base + k);
 }
 
 static void finish_sweep(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   cudaStream_t st = ctx->stream;
-  const int TB = 256;
-  R->edge_scan.ensure((size_t)R->n_edges + 2, st);
-  R->node_scan.ensure((size_t)R->n_nodes + 2, st);
-  exclusive_scan<uint8_t, int32_t>(ctx, R->edge_flag.p, R->n_edges, R->edge_scan.p, R->scan_tmp);
-  exclusive_scan<uint8_t, int32_t>(ctx, R->node_flag.p, R->n_nodes, R->node_scan.p, R->scan_tmp);
+  static_assert(SCAN_ITEMS == 8, "compact_tiles_kernel reads 8 flags per thread as one 64-bit word");
+  const int64_t et = (R->n_edges + SCAN_TILE - 1) / SCAN_TILE, nt = (R->n_nodes + SCAN_TILE - 1) / SCAN_TILE;
+  R->edge_scan.ensure((size_t)et + 2, st);  // tile offsets, [et] = total
+  R->node_scan.ensure((size_t)nt + 2, st);
+  RQ_CUDA(cudaMemsetAsync(R->edge_scan.p, 0, sizeof(int32_t), st));  // totals of empty arrays
+  RQ_CUDA(cudaMemsetAsync(R->node_scan.p, 0, sizeof(int32_t), st));
+  if (et) {
+    scan_tile_sums_kernel<uint8_t, int32_t><<<(unsigned)et, SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, R->edge_scan.p);
+    scan_sums_kernel<int32_t><<<1, 1024, 0, st>>>(R->edge_scan.p, et);
+  }
+  if (nt) {
+    scan_tile_sums_kernel<uint8_t, int32_t><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(R->node_flag.p, R->n_nodes, R->node_scan.p);
+    scan_sums_kernel<int32_t><<<1, 1024, 0, st>>>(R->node_scan.p, nt);
+  }
   int32_t ne_hits = 0, nn_hits = 0;
   unsigned long long stats[2] = {0, 0};
-  RQ_CUDA(cudaMemcpyAsync(&ne_hits, R->edge_scan.p + R->n_edges, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  RQ_CUDA(cudaMemcpyAsync(&nn_hits, R->node_scan.p + R->n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaMemcpyAsync(&ne_hits, R->edge_scan.p + et, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaMemcpyAsync(&nn_hits, R->node_scan.p + nt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RQ_CUDA(cudaMemcpyAsync(stats, R->stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
   RQ_CUDA(cudaStreamSynchronize(st));
   R->n_edge_hits = ne_hits;
@@ -488,9 +517,9 @@ static void finish_sweep(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   R->n_pair_tests = (int64_t)stats[1];
   R->edge_list.ensure((size_t)ne_hits + 1, st);
   R->node_list.ensure((size_t)nn_hits + 1, st);
-  if (R->n_edges) compact_flags_kernel<<<div_up(R->n_edges, TB), TB, 0, st>>>(R->edge_flag.p, R->edge_scan.p, R->n_edges, R->edge_list.p);
-  if (R->n_nodes) compact_flags_kernel<<<div_up(R->n_nodes, TB), TB, 0, st>>>(R->node_flag.p, R->node_scan.p, R->n_nodes, R->node_list.p);
-  post_launch(ctx, 2);
+  if (et) compact_tiles_kernel<<<(unsigned)et, SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, R->edge_scan.p, R->edge_list.p);
+  if (nt) compact_tiles_kernel<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(R->node_flag.p, R->n_nodes, R->node_scan.p, R->node_list.p);
+  post_launch(ctx, 6);
 }
 
 static void prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
