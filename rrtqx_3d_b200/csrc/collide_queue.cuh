@@ -110,13 +110,13 @@ static inline SphCoverBufs &cover_bufs(rrtqx_ctx *ctx) {
   return *it->second;
 }
 
-// Batches below this many items keep the thread-per-edge kernels (the cover build is ~10 small launches).
+// Batches below this many items keep the thread-per-edge kernels (the grid / cover build and the extra launches
+// are ~40 us).  Read on every call so that tests can switch paths: RRTQX_EDGE_NO_QUEUE=1 forces the thread-per-edge
+// kernels, RRTQX_COVER_MIN_ITEMS=n moves the threshold.
 static inline int64_t cover_min_items() {
-  static const int64_t v = [] {
-    const char *e = getenv("RRTQX_COVER_MIN_ITEMS");
-    return e ? (int64_t)atoll(e) : (int64_t)16384;
-  }();
-  return getenv("RRTQX_EDGE_NO_QUEUE") ? INT64_MAX : v;
+  if (getenv("RRTQX_EDGE_NO_QUEUE")) return INT64_MAX;
+  const char *e = getenv("RRTQX_COVER_MIN_ITEMS");
+  return e ? (int64_t)atoll(e) : (int64_t)16384;
 }
 
 // ---------------------------------------------------------------- pair queue

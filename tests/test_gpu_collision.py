@@ -355,3 +355,37 @@ def test_edge_check_cover_lists_short_edges(ctx):
         assert got[:len(got) - 4:97].all()
         if name in ("c3", "tiny"):
             assert 0 < got.sum() < len(got)
+
+
+def test_two_stage_and_thread_per_edge_paths_agree(ctx):
+    """The same edge batch and add sweep through the two-stage kernels (default for large batches), the
+    thread-per-edge grid kernels (RRTQX_EDGE_NO_QUEUE=1) and the two-stage kernels forced onto a small batch
+    (RRTQX_COVER_MIN_ITEMS=1): identical flags / id lists, and equal to the oracle."""
+    import os
+    pts, _, _ = W.c2_workload(12000, 1)
+    t, src, dst, parent = _neighbour_graph(ctx, pts, 1.6)
+    centers, radii = W.c3_obstacles(64)
+    S = SphereSet(ctx, centers, radii)
+    sph, ns = oracle.make_spheres(centers, radii)
+    E = EdgeSet(t)
+    E.upload(src, dst, parent)
+    ids = np.arange(len(radii), dtype=np.int32)
+    small = slice(0, 6000)                      # 4096 <= n < 16384: thread-per-edge grid kernel by default
+    want = _orc_edges(sph, ns, pts, src, dst, W.ROBOT_RADIUS)
+    results = {}
+    for mode, env in (("default", {}), ("no_queue", {"RRTQX_EDGE_NO_QUEUE": "1"}), ("forced", {"RRTQX_COVER_MIN_ITEMS": "1"})):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            full = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS)
+            part = edge_check_batch(t, S, src[small], dst[small], W.ROBOT_RADIUS)
+            sw = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA)
+            results[mode] = (full, part, *sw.fetch())
+        finally:
+            for k in env:
+                del os.environ[k]
+    for mode, (full, part, be, on) in results.items():
+        assert np.array_equal(full, want), mode
+        assert np.array_equal(part, want[small]), mode
+        assert np.array_equal(be, results["default"][2]) and np.array_equal(on, results["default"][3]), mode
+    assert 0 < want.sum() < len(want) and len(results["default"][2]) > 0
