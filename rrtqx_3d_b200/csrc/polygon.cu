@@ -5,6 +5,8 @@
 //   Dubins explicitEdgeCheck     DRRT_DubinsEdge_functions.jl:750-774
 //   explicitEdgeCheck(C, edge)   DRRT.jl:1660-1678   (OR over the obstacle list)
 // Every operation is individually rounded FP64 in the reference's order.
+#include <cstdlib>
+
 #include "objects.cuh"
 
 namespace rrtqx {
@@ -99,7 +101,7 @@ segment_check_2d_kernel(PolyView P, int ignore_active, const double *__restrict_
 // start->end test (radius rho + 2 r_turn) over 32 obstacles at a time; each surviving obstacle
 // is then tested against the trajectory segments, 32 segments per trip.
 __global__ void __launch_bounds__(256)
-dubins_check_kernel(PolyView P, int ignore_active, const double *__restrict__ starts, const double *__restrict__ ends,
+dubins_check_v1_kernel(PolyView P, int ignore_active, const double *__restrict__ starts, const double *__restrict__ ends,
                     const int64_t *__restrict__ tptr, const double *__restrict__ traj, int64_t n_edges, double rho,
                     double rho_coarse, uint8_t *__restrict__ out) {
   const int lane = lane_id();
@@ -115,6 +117,79 @@ dubins_check_kernel(PolyView P, int ignore_active, const double *__restrict__ st
     while (m && !collide) {
       const int ob = o0 + __ffs(m) - 1;
       m &= m - 1;
+      for (int64_t i0 = t0 + 1; i0 < t1 && !collide; i0 += 32) {  // for i = 2:size(trajectory,1)  :767-771
+        const int64_t i = i0 + lane;
+        bool hit = false;
+        if (i < t1)
+          hit = edge_check_2d(P, ob, ignore_active, traj[2 * (i - 1)], traj[2 * (i - 1) + 1], traj[2 * i],
+                              traj[2 * i + 1], rho);
+        collide = __any_sync(FULL, hit);
+      }
+    }
+  }
+  if (lane == 0) out[e] = collide ? 1 : 0;
+}
+
+// Same check, coarse stage restructured.  In the first form every lane ran the whole coarse test of its
+// obstacle, so the few obstacles that pass the bounding-circle part made the warp wait through their polygon
+// loops, trip after trip.  Here the circle part runs lane-parallel over 32 obstacles, and the polygon part of
+// the survivors is spread over the lanes: 8 lanes per obstacle, one polygon edge each, 4 obstacles per round.
+// The same predicates are evaluated on the same operands (explicitEdgeCheck2D :1536-1578); only the order of an
+// OR changes.
+__global__ void __launch_bounds__(256)
+dubins_check_kernel(PolyView P, int ignore_active, const double *__restrict__ starts, const double *__restrict__ ends,
+                    const int64_t *__restrict__ tptr, const double *__restrict__ traj, int64_t n_edges, double rho,
+                    double rho_coarse, uint8_t *__restrict__ out) {
+  const int lane = lane_id();
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n_edges) return;
+  const double sx = starts[2 * e], sy = starts[2 * e + 1], ex = ends[2 * e], ey = ends[2 * e + 1];
+  const int64_t t0 = tptr[e], t1 = tptr[e + 1];
+  const double rc2 = __dmul_rn(rho_coarse, rho_coarse);
+  const int sub = lane >> 3, j0 = lane & 7;
+  bool collide = false;
+  for (int o0 = 0; o0 < P.n && !collide; o0 += 32) {
+    const int o = o0 + lane;
+    int st = 0;  // 0: coarse test fails, 1: passes (ball), 3: polygon part still to do
+    if (o < P.n && (ignore_active || P.active[o])) {
+      const double2 c = P.center[o];
+      const double d2 = dist2_point_segment_2d(c.x, c.y, sx, sy, ex, ey);  // :1536
+      const double rr = __dadd_rn(rho_coarse, P.radius[o]);
+      if (!(d2 > __dmul_rn(rr, rr))) {  // :1537-1539
+        const int kind = P.kind[o];
+        if (kind == 1) st = 1;
+        else if (kind == 3 && P.vptr[o + 1] - P.vptr[o] >= 2) st = 3;  // :1551-1553
+      }
+    }
+    unsigned pass = __ballot_sync(FULL, st == 1), pend = __ballot_sync(FULL, st == 3);
+    while (pend) {  // polygon part of the coarse test, up to 4 obstacles per round
+      unsigned mm = pend;
+      int ob = -1;
+      for (int k = 0; k <= sub && mm; ++k) {
+        ob = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (k < sub) ob = -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pend &= pend - 1;  // the 4 lowest candidates are taken (x & (x-1) of 0 is 0)
+      bool hit = false;
+      if (ob >= 0) {
+        const int64_t v0 = P.vptr[o0 + ob], v1 = P.vptr[o0 + ob + 1];
+        for (int64_t i = v0 + j0; i < v1 && !hit; i += 8) {  // polygon edge (verts[i-1], verts[i]), first one wraps
+          const double2 A = P.verts[i == v0 ? v1 - 1 : i - 1], B = P.verts[i];
+          hit = segment_dist2_2d(sx, sy, ex, ey, A.x, A.y, B.x, B.y) < rc2;
+        }
+      }
+      const unsigned hm = __ballot_sync(FULL, hit);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int obk = __shfl_sync(FULL, ob, 8 * k);
+        if (obk >= 0 && ((hm >> (8 * k)) & 0xffu)) pass |= 1u << obk;
+      }
+    }
+    while (pass && !collide) {  // obstacles that passed the coarse test: every trajectory segment, 32 per trip
+      const int ob = o0 + __ffs(pass) - 1;
+      pass &= pass - 1;
       for (int64_t i0 = t0 + 1; i0 < t1 && !collide; i0 += 32) {  // for i = 2:size(trajectory,1)  :767-771
         const int64_t i = i0 + lane;
         bool hit = false;
@@ -268,8 +343,12 @@ rrtqx_status rrtqx_dubins_edge_check_batch(rrtqx_polygons *p, const double *star
       PhaseScope ph(ctx, "dubins_check");
       // S.robotRadius + 2*S.minTurningRadius (DRRT_DubinsEdge_functions.jl:758)
       const double rho_coarse = robot_radius + 2 * min_turn_radius;
-      dubins_check_kernel<<<div_up(n_edges * 32, 256), 256, 0, st>>>(p->view(), (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
-                                                                    ds, de, dp, dt, n_edges, robot_radius, rho_coarse, dout);
+      if (getenv("RRTQX_DUBINS_CHECK_V1"))
+        dubins_check_v1_kernel<<<div_up(n_edges * 32, 256), 256, 0, st>>>(p->view(), (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
+                                                                         ds, de, dp, dt, n_edges, robot_radius, rho_coarse, dout);
+      else
+        dubins_check_kernel<<<div_up(n_edges * 32, 256), 256, 0, st>>>(p->view(), (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
+                                                                      ds, de, dp, dt, n_edges, robot_radius, rho_coarse, dout);
       post_launch(ctx);
     }
     if (!od) from_device(ctx, collide_out, dout, (size_t)n_edges);
