@@ -646,7 +646,30 @@ def main():
                 if it >= 3:
                     et.append(ctx.last_phase_ms("edge_check"))
             ems = float(np.mean(et))
-            line["edge_batch"] = {"workload": "explicitEdgeCheck(S, edge) for every C3 edge against all 256 spheres (device-resident)",
+            # CPU side of the same batch: the oracle's explicitEdgeCheck loop (front-to-back over the obstacle list,
+            # early exit) on a bounded sample of the edges, all host threads
+            cpu_edge = None
+            if not args.no_cpu:
+                import oracle
+                nthr = os.cpu_count() or 1
+                sph, ns = oracle.make_spheres(centers, radii)
+                hp = np.ascontiguousarray(pts)
+
+                def _cpu_edges(n):
+                    o = np.zeros(n, dtype=np.uint8)
+                    t0 = time.perf_counter()
+                    oracle.lib().orc_edge_check_batch(sph, ns, oracle._p(hp, oracle.c_f64p), 3, oracle._p(src, oracle.c_i32p),
+                                                      oracle._p(dst, oracle.c_i32p), 0, n, W.ROBOT_RADIUS, 0,
+                                                      oracle._p(o, oracle.c_u8p), nthr)
+                    return time.perf_counter() - t0, o
+                dt, _ = _cpu_edges(min(len(src), 20000 * nthr))
+                n_s = int(min(len(src), max(20000 * nthr, min(len(src), 20000 * nthr) / dt * 4.0)))
+                dt, flags_cpu = _cpu_edges(n_s)
+                cpu_edge = {"value": n_s / dt, "unit": "edges/s", "cores": nthr, "kind": "port",
+                            "sample": f"first {n_s} of {len(src)} C3 edges vs 256 spheres, {dt:.1f}s timed",
+                            "matches_gpu": bool(np.array_equal(flags_cpu, dflag[:n_s].cpu().numpy()))}
+            line["edge_batch"] = {"cpu_baseline": cpu_edge,
+                                  "workload": "explicitEdgeCheck(S, edge) for every C3 edge against all 256 spheres (device-resident)",
                                   "edges": len(src), "obstacles": args.sweep_obstacles, "ms": ems,
                                   "edges_per_s": len(src) / (ems / 1e3),
                                   "edge_obstacle_pairs_per_s": len(src) * args.sweep_obstacles / (ems / 1e3),
