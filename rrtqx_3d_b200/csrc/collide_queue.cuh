@@ -110,13 +110,15 @@ static inline SphCoverBufs &cover_bufs(rrtqx_ctx *ctx) {
   return *it->second;
 }
 
-// Batches below this many items keep the thread-per-edge kernels (the grid / cover build and the extra launches
-// are ~40 us).  Read on every call so that tests can switch paths: RRTQX_EDGE_NO_QUEUE=1 forces the thread-per-edge
-// kernels, RRTQX_COVER_MIN_ITEMS=n moves the threshold.
-static inline int64_t cover_min_items() {
+// Batches below the threshold keep the thread-per-edge kernels: the cover build and the extra launches cost
+// ~40 us, the two-stage path saves ~19 ns per 1000 edges in the batch check (break-even ~2e6 edges) and ~44 ns
+// per 1000 items in the add sweep (break-even ~1e6).  Read on every call so that tests can switch paths:
+// RRTQX_EDGE_NO_QUEUE=1 forces the thread-per-edge kernels, RRTQX_COVER_MIN_ITEMS=n moves the threshold.
+constexpr int64_t PQ_MIN_ITEMS_BATCH = (int64_t)1 << 21, PQ_MIN_ITEMS_SWEEP = (int64_t)1 << 20;
+static inline int64_t cover_min_items(int64_t dflt) {
   if (getenv("RRTQX_EDGE_NO_QUEUE")) return INT64_MAX;
   const char *e = getenv("RRTQX_COVER_MIN_ITEMS");
-  return e ? (int64_t)atoll(e) : (int64_t)16384;
+  return e ? (int64_t)atoll(e) : dflt;
 }
 
 // ---------------------------------------------------------------- pair queue

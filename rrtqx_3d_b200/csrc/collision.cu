@@ -245,7 +245,7 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
       b.cstart.ensure(SG_MAX_CELLS + 4, st);
       b.grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)b.grid.p;
-      const bool use_queue = n_edges >= cover_min_items() && n_edges < ((int64_t)1 << 32);
+      const bool use_queue = n_edges >= cover_min_items(PQ_MIN_ITEMS_BATCH) && n_edges < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, (use_queue && spheres->n <= COV_MAX_OBSTACLES) ? 1 : 0);
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);

@@ -565,7 +565,7 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       SphGrid *dG = (SphGrid *)R->grid.p;
       R->ob_frec2.ensure((size_t)n_obs + 1, st);
       const int64_t work = E->n_edges + E->n_nodes;
-      const bool use_queue = work >= cover_min_items() && work < ((int64_t)1 << 32);
+      const bool use_queue = work >= cover_min_items(PQ_MIN_ITEMS_SWEEP) && work < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
                                              R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, (use_queue && n_obs <= COV_MAX_OBSTACLES) ? 1 : 0);
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;

@@ -319,7 +319,8 @@ def test_resident_edge_set_grows_with_the_planner(ctx):
 
 
 def test_edge_check_cover_lists_short_edges(ctx):
-    """Large batches of SHORT edges take the warp-queue kernel with cover lists (csrc/collide_queue.cuh): one
+    """Very large batches of SHORT edges take the two-stage kernels with cover lists (csrc/collide_queue.cuh; forced
+    here at test size): one
     fine-grid cell list per edge instead of the coarse rows.  Mixed with long, zero-length and out-of-box edges,
     against obstacle sets that keep the cover (C3-style), overflow its budget (huge spheres: coarse rows), are
     tiny compared with the box, or sit outside the tree's box; booleans bit-exact, with and without the FMA dot."""
@@ -344,23 +345,28 @@ def test_edge_check_cover_lists_short_edges(ctx):
         "mixed": (np.vstack([rng.uniform(-20, 20, (60, 3)), [[1e3, 1e3, 1e3]], [[np.nan, 0.0, 0.0]]]),
                   np.concatenate([rng.uniform(0.5, 3.0, 60), [1.0], [1.0]])),
     }
-    for name, (c, r) in sets.items():
-        c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
-        S = SphereSet(ctx, c, r)
-        sph, ns = oracle.make_spheres(c, r)
-        for fma in (0, 1):
-            got = edge_check_batch(t2, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_FMA_DOT if fma else 0)
-            want = _orc_edges(sph, ns, pts2, src, dst, W.ROBOT_RADIUS, fma)
-            assert np.array_equal(got, want), (name, fma, int((got != want).sum()))
-        assert got[:len(got) - 4:97].all()
-        if name in ("c3", "tiny"):
-            assert 0 < got.sum() < len(got)
+    import os
+    os.environ["RRTQX_COVER_MIN_ITEMS"] = "1"   # the two-stage path is the default only above ~2e6 edges
+    try:
+        for name, (c, r) in sets.items():
+            c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
+            S = SphereSet(ctx, c, r)
+            sph, ns = oracle.make_spheres(c, r)
+            for fma in (0, 1):
+                got = edge_check_batch(t2, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_FMA_DOT if fma else 0)
+                want = _orc_edges(sph, ns, pts2, src, dst, W.ROBOT_RADIUS, fma)
+                assert np.array_equal(got, want), (name, fma, int((got != want).sum()))
+            assert got[:len(got) - 4:97].all()
+            if name in ("c3", "tiny"):
+                assert 0 < got.sum() < len(got)
+    finally:
+        del os.environ["RRTQX_COVER_MIN_ITEMS"]
 
 
 def test_two_stage_and_thread_per_edge_paths_agree(ctx):
-    """The same edge batch and add sweep through the two-stage kernels (default for large batches), the
-    thread-per-edge grid kernels (RRTQX_EDGE_NO_QUEUE=1) and the two-stage kernels forced onto a small batch
-    (RRTQX_COVER_MIN_ITEMS=1): identical flags / id lists, and equal to the oracle."""
+    """The same edge batch and add sweep through the library's own choice (thread-per-edge grid kernels at this
+    size; the two-stage kernels take over above ~1e6 items), the thread-per-edge kernels forced
+    (RRTQX_EDGE_NO_QUEUE=1) and the two-stage kernels forced (RRTQX_COVER_MIN_ITEMS=1): identical flags / id lists, and equal to the oracle."""
     import os
     pts, _, _ = W.c2_workload(12000, 1)
     t, src, dst, parent = _neighbour_graph(ctx, pts, 1.6)
