@@ -25,6 +25,24 @@ def test_header_and_binding_declare_the_same_symbols():
     assert hs == sorted(A.SIGNATURES.keys())
 
 
+def test_julia_module_binds_only_declared_symbols():
+    """julia/RRTQXGpu.jl cannot be executed here (no Julia in the image); at least every symbol it `ccall`s must be
+    one the header declares, and its block structure must be balanced."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "julia", "RRTQXGpu.jl")).read()
+    bound = set(re.findall(r":(rrtqx_[a-z0-9_]+)", src))
+    assert len(bound) >= 30
+    assert bound <= set(header_symbols()), sorted(bound - set(header_symbols()))
+    depth = 0
+    for line in src.splitlines():
+        code = re.sub(r'"(\\.|[^"\\])*"', '""', line).split("#")[0]
+        code = re.sub(r"\[[^\]]*\]", "[]", code)          # a[end], comprehensions
+        for tok in re.findall(r"\b(function|if|for|while|let|struct|module|begin|do|try|quote|macro|end)\b", code):
+            depth += -1 if tok == "end" else 1
+            assert depth >= 0, line
+    assert depth == 0
+
+
 def test_library_exports_every_declared_symbol():
     L = A.lib()
     out = subprocess.run(["nm", "-D", "--defined-only", A.LIB_PATH], capture_output=True, text=True).stdout
