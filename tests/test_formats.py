@@ -96,3 +96,20 @@ def test_path_kd_data_and_collision_node_writers():
     order = np.array([0, 2, 1])
     out = F.dump_to_string(F.save_rrt_nodes_collision, pos[:3], order, [0.0, np.inf, 2.0], [1.0, 5.0, np.nan])
     assert out == "0.0,0.0,0.0,0.0\n4.5,-1.0,2.0,NaN\n1.0,2.0,3.0,5.0\n"
+
+
+def test_julia_float_round_trips_random_bit_patterns():
+    """Shortest round-trip printing: parsing the text gives back the same double, for random bit patterns (all
+    exponents, subnormals included) and for values around the fixed/exponential switch points."""
+    rng = np.random.default_rng(12)
+    bits = rng.integers(0, 2 ** 63, 20000, dtype=np.int64).astype(np.uint64) | (rng.integers(0, 2, 20000).astype(np.uint64) << np.uint64(63))
+    xs = bits.view(np.float64)
+    xs = xs[np.isfinite(xs)]
+    edge = np.array([1e-5, 9.999999999999999e-5, 1e-4, 1.0000000000000002e-4, 999999.9999999999, 1e6, 1000000.0000000001,
+                     9999999.999999998, 1e7, 123456.7, 0.1 + 0.2, 5e-324, 1.7976931348623157e308, 2.2250738585072014e-308])
+    for x in np.concatenate([xs, edge, -edge]):
+        s = F.julia_float(float(x))
+        assert float(s) == x, (x, s)
+        assert ("e" in s) == (not (1e-4 <= abs(x) < 1e6)), (x, s)      # fixed notation exactly on [1e-4, 1e6)
+        mant = s.lstrip("-").split("e")[0]
+        assert "." in mant and not mant.endswith(".") and not mant.startswith("."), s
