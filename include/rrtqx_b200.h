@@ -72,6 +72,11 @@ RRTQX_API rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream,
                                         rrtqx_ctx **out);
 RRTQX_API rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx);
 RRTQX_API const char *rrtqx_last_error(const rrtqx_ctx *ctx);
+/* The diagnostic RRTQX_* environment switches are read
+ * once, by rrtqx_ctx_create; this re-reads them for `ctx` (tests and A/B runs
+ * that change a switch between calls).  No call on the hot path touches the
+ * environment. */
+RRTQX_API rrtqx_status rrtqx_ctx_reload_tuning(rrtqx_ctx *ctx);
 RRTQX_API rrtqx_status rrtqx_ctx_sync(rrtqx_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 RRTQX_API rrtqx_status rrtqx_ctx_kernel_launches(const rrtqx_ctx *ctx,
@@ -263,7 +268,9 @@ RRTQX_API rrtqx_status rrtqx_node_check_batch(rrtqx_ctx *ctx,
  *                            -> fwd_collide[], rev_collide[]  (the test is not symmetric)
  * `capacity` = length of the four neighbour arrays; *n_neighbors receives the
  * full count (if it exceeds capacity only the first `capacity` are written).
- * At most 768 obstacles; d == 3 for the edge checks (other d: flags are 0).
+ * At most 768 ACTIVE obstacles (inactive entries of an ever-growing list are
+ * compacted away, once per obstacle-set change); d == 3 for the edge checks
+ * (other d: flags are 0).
  * Results arrive through mapped pinned memory: one launch, one synchronise. */
 RRTQX_API rrtqx_status rrtqx_extend_query(
     rrtqx_tree *tree, const rrtqx_spheres *spheres, const double *point,

@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
         "orc_kd_empty_range_list": (None, [c_u8p, c_i32p, i64]),
         "orc_kd_find_within_range_naive": (i64, [vp, f64, c_f64p, c_i32p, c_f64p, i64]),
         "orc_kd_range_batch": (i64, [vp, f64, c_f64p, i64, i64, c_i32p, c_i64p, c_i32p, c_f64p, i64, cint]),
+        "orc_kd_range_batch_once": (i64, [vp, f64, c_f64p, i64, i64, c_i32p, c_i64p, cint, C.POINTER(vp)]),
+        "orc_range_lists_copy": (None, [vp, c_i32p, c_f64p]),
+        "orc_range_lists_free": (None, [vp]),
         "orc_kd_nearest_batch": (None, [vp, c_f64p, i64, i64, c_i32p, c_f64p, cint]),
         "orc_dist_point_to_segment": (f64, [c_f64p, c_f64p, c_f64p, cint, cint]),
         "orc_edge_check_sphere": (cint, [C.POINTER(Sphere), c_f64p, c_f64p, f64, cint]),
@@ -218,14 +221,32 @@ class KDTree:
         return idx[:ln].copy(), key[:ln].copy()
 
     def range_batch(self, r, queries, want_lists=True, nthreads=1):
-        """CSR results for all queries: (counts, offsets, idx, key)."""
+        """CSR results for all queries: (counts, offsets, idx, key).  ONE tree traversal per query, like the
+        reference's kdFindWithinRange (hits go to per-thread growing buffers and are copied out afterwards)."""
+        q = _f64(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        counts = np.zeros(nq, dtype=np.int32)
+        if not want_lists:
+            self.L.orc_kd_range_batch(self.h, float(r), _p(q, c_f64p), 0, nq, _p(counts, c_i32p),
+                                      None, None, None, 0, nthreads)
+            return counts, None, None, None
+        offsets = np.zeros(nq + 1, dtype=np.int64)
+        lists = C.c_void_p()
+        total = self.L.orc_kd_range_batch_once(self.h, float(r), _p(q, c_f64p), 0, nq, _p(counts, c_i32p),
+                                               _p(offsets, c_i64p), nthreads, C.byref(lists))
+        idx = np.empty(max(total, 1), dtype=np.int32)
+        key = np.empty(max(total, 1), dtype=np.float64)
+        self.L.orc_range_lists_copy(lists, _p(idx, c_i32p), _p(key, c_f64p))
+        self.L.orc_range_lists_free(lists)
+        return counts, offsets, idx[:total], key[:total]
+
+    def range_batch_two_pass(self, r, queries, nthreads=1):
+        """Count pass + fill pass (two traversals per query); kept to cross-check range_batch."""
         q = _f64(queries).reshape(-1, self.d)
         nq = q.shape[0]
         counts = np.zeros(nq, dtype=np.int32)
         total = self.L.orc_kd_range_batch(self.h, float(r), _p(q, c_f64p), 0, nq, _p(counts, c_i32p),
                                           None, None, None, 0, nthreads)
-        if not want_lists:
-            return counts, None, None, None
         offsets = np.zeros(nq + 1, dtype=np.int64)
         idx = np.empty(max(total, 1), dtype=np.int32)
         key = np.empty(max(total, 1), dtype=np.float64)

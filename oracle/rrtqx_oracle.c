@@ -565,6 +565,113 @@ int64_t orc_kd_range_batch(const orc_kdtree *t, double range, const double *q,
   return total;
 }
 
+/* Single-traversal batch driver (the timed CPU arm): every query walks the tree ONCE, as kdFindWithinRange does
+ * (kdTree_general.jl:889-919), appending (node, key) to a per-thread growing buffer -- the JList pushes of the
+ * reference.  The per-thread buffers are handed back as an opaque object and copied out afterwards. */
+struct orc_range_lists {
+  int nthreads;
+  int64_t total;
+  int32_t *idx[256];
+  double *key[256];
+  int64_t len[256];
+};
+
+typedef struct {
+  batch_job j;
+  int32_t *idx;
+  double *key;
+  int64_t cap, len;
+} once_job;
+
+static void *range_once_worker(void *arg) {
+  once_job *o = (once_job *)arg;
+  batch_job *j = &o->j;
+  const orc_kdtree *t = j->t;
+  uint8_t *marks = (uint8_t *)calloc(t->n ? t->n : 1, 1);
+  o->cap = 1 << 16;
+  o->len = 0;
+  o->idx = (int32_t *)malloc(sizeof(int32_t) * o->cap);
+  o->key = (double *)malloc(sizeof(double) * o->cap);
+  for (int64_t i = j->q0; i < j->q1; ++i) {
+    /* a result list cannot exceed the tree size: make room for the worst case of THIS query only when the
+     * remaining space is smaller than the largest list seen so far times two (amortised doubling) */
+    range_list L = {marks, o->idx + o->len, o->key + o->len, o->cap - o->len, 0, 0, 0};
+    if (t->n) kd_range_impl(t, j->range, j->q + i * t->d, &L);
+    if (L.overflow) { /* rare: grow and redo this one query (marks cleared first) */
+      memset(marks, 0, t->n);
+      while (o->cap - o->len < L.len) o->cap *= 2;
+      o->idx = (int32_t *)realloc(o->idx, sizeof(int32_t) * o->cap);
+      o->key = (double *)realloc(o->key, sizeof(double) * o->cap);
+      range_list L2 = {marks, o->idx + o->len, o->key + o->len, o->cap - o->len, 0, 0, 0};
+      kd_range_impl(t, j->range, j->q + i * t->d, &L2);
+      L = L2;
+    }
+    j->counts[i] = (int32_t)L.len;
+    orc_kd_empty_range_list(marks, o->idx + o->len, L.len);
+    o->len += L.len;
+    if (o->cap - o->len < 4096) { /* keep head-room so that the redo above stays rare */
+      o->cap *= 2;
+      o->idx = (int32_t *)realloc(o->idx, sizeof(int32_t) * o->cap);
+      o->key = (double *)realloc(o->key, sizeof(double) * o->cap);
+    }
+  }
+  free(marks);
+  return NULL;
+}
+
+int64_t orc_kd_range_batch_once(const orc_kdtree *t, double range, const double *q, int64_t q0, int64_t q1,
+                                int32_t *counts, int64_t *offsets, int nthreads, orc_range_lists **out) {
+  int64_t n = q1 - q0;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (n < nthreads) nthreads = n > 0 ? (int)n : 1;
+  once_job jobs[256];
+  pthread_t th[256];
+  for (int k = 0; k < nthreads; ++k) {
+    memset(&jobs[k], 0, sizeof(once_job));
+    jobs[k].j.t = t;
+    jobs[k].j.range = range;
+    jobs[k].j.q = q + q0 * t->d;
+    jobs[k].j.counts = counts;
+    jobs[k].j.q0 = n * k / nthreads;
+    jobs[k].j.q1 = n * (k + 1) / nthreads;
+  }
+  if (nthreads == 1) {
+    range_once_worker(&jobs[0]);
+  } else {
+    for (int k = 0; k < nthreads; ++k) pthread_create(&th[k], NULL, range_once_worker, &jobs[k]);
+    for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+  }
+  orc_range_lists *R = (orc_range_lists *)calloc(1, sizeof(orc_range_lists));
+  R->nthreads = nthreads;
+  for (int k = 0; k < nthreads; ++k) {
+    R->idx[k] = jobs[k].idx; R->key[k] = jobs[k].key; R->len[k] = jobs[k].len;
+    R->total += jobs[k].len;
+  }
+  if (offsets) { /* threads own consecutive query ranges, so the concatenation is in query order */
+    int64_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) { offsets[i] = acc; acc += counts[i]; }
+    offsets[n] = acc;
+  }
+  *out = R;
+  return R->total;
+}
+
+void orc_range_lists_copy(const orc_range_lists *R, int32_t *idx, double *key) {
+  int64_t acc = 0;
+  for (int k = 0; k < R->nthreads; ++k) {
+    if (idx) memcpy(idx + acc, R->idx[k], sizeof(int32_t) * R->len[k]);
+    if (key) memcpy(key + acc, R->key[k], sizeof(double) * R->len[k]);
+    acc += R->len[k];
+  }
+}
+
+void orc_range_lists_free(orc_range_lists *R) {
+  if (!R) return;
+  for (int k = 0; k < R->nthreads; ++k) { free(R->idx[k]); free(R->key[k]); }
+  free(R);
+}
+
 static void *nearest_worker(void *arg) {
   batch_job *j = (batch_job *)arg;
   uint64_t evals = 0;

@@ -95,6 +95,14 @@ int64_t orc_kd_range_batch(const orc_kdtree *t, double range, const double *q,
                            int64_t q0, int64_t q1, int32_t *counts,
                            int64_t *offsets, int32_t *idx_out, double *key_out,
                            int64_t cap, int nthreads);
+/* Single-traversal form of the same batch (what bench.py's CPU arm times): one walk per query, results in
+ * per-thread growing buffers; counts[i] / offsets[i] (nq+1) as above.  Returns the total; the lists are copied
+ * out (query order) with orc_range_lists_copy and released with orc_range_lists_free. */
+typedef struct orc_range_lists orc_range_lists;
+int64_t orc_kd_range_batch_once(const orc_kdtree *t, double range, const double *q, int64_t q0, int64_t q1,
+                                int32_t *counts, int64_t *offsets, int nthreads, orc_range_lists **out);
+void orc_range_lists_copy(const orc_range_lists *R, int32_t *idx, double *key);
+void orc_range_lists_free(orc_range_lists *R);
 void orc_kd_nearest_batch(orc_kdtree *t, const double *q, int64_t q0,
                           int64_t q1, int32_t *idx_out, double *dist_out,
                           int nthreads);

@@ -15,8 +15,7 @@ struct NearestScratchHolder {
   DevBuf<int32_t> idx;
   DevBuf<double> dist;
 };
-static std::map<rrtqx_tree *, NearestScratchHolder *> g_nearest_scratch;
-static std::mutex g_nearest_mutex;
+static const char g_nearest_tag = 0;  // key of the per-tree nearest-query scratch (rrtqx_tree::scratch)
 
 namespace {
 template <typename F>
@@ -61,6 +60,7 @@ rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream, rrtqx_ctx **out
     if (prop.major != 10)
       throw Error(RRTQX_ERR_CUDA, std::string("this library is built for sm_100a only; device is ") + prop.name);
     rrtqx_ctx *c = new rrtqx_ctx();
+    c->tune.load();  // the only place (with rrtqx_ctx_reload_tuning) where the environment is read
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cuda_stream) {
@@ -83,9 +83,16 @@ rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx) {
       if (kv.second.a) cudaEventDestroy(kv.second.a);
       if (kv.second.b) cudaEventDestroy(kv.second.b);
     }
+    ctx->scratch.clear();  // device buffers of the collision / sweep paths, while the device is bound
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
   });
+}
+
+rrtqx_status rrtqx_ctx_reload_tuning(rrtqx_ctx *ctx) {
+  if (!ctx) return RRTQX_ERR_INVALID;
+  ctx->tune.load();
+  return RRTQX_OK;
 }
 
 const char *rrtqx_last_error(const rrtqx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
@@ -169,8 +176,8 @@ rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d, int32_t num_wraps, con
     t->ctx = ctx;
     t->d = d;
     t->wrap.num_wraps = num_wraps;
-    if (const char *e = getenv("RRTQX_GRID_OCCUPANCY")) { double v = atof(e); if (v > 0.0) t->occupancy = v; }
-    if (const char *e = getenv("RRTQX_GRID_ASPECT")) { double v = atof(e); if (v >= 1.0) t->aspect = v; }
+    if (ctx->tune.grid_occupancy > 0.0) t->occupancy = ctx->tune.grid_occupancy;
+    if (ctx->tune.grid_aspect >= 1.0) t->aspect = ctx->tune.grid_aspect;
     for (int i = 0; i < num_wraps; ++i) {
       if (wraps[i] < 0 || wraps[i] >= d) { delete t; throw Error(RRTQX_ERR_INVALID, "wrap dimension out of range"); }
       t->wrap.wraps[i] = wraps[i];
@@ -186,13 +193,7 @@ rrtqx_status rrtqx_tree_destroy(rrtqx_tree *tree) {
   return guarded(ctx, [&] {
     bind_device(ctx);
     RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    {
-      std::lock_guard<std::mutex> lk(g_nearest_mutex);
-      auto it = g_nearest_scratch.find(tree);
-      if (it != g_nearest_scratch.end()) { delete it->second; g_nearest_scratch.erase(it); }
-    }
-    extend_state_drop(tree);
-    delete tree;
+    delete tree;  // frees the per-tree scratch (nearest sort buffers, extend_query state) with it
   });
 }
 
@@ -415,14 +416,8 @@ rrtqx_status rrtqx_nearest_batch(rrtqx_tree *tree, const double *queries, int64_
   return guarded(ctx, [&] {
     bind_device(ctx);
     RQ_REQUIRE(queries != nullptr || n_queries == 0, "queries is NULL");
-    NearestScratchHolder *h;
-    {
-      std::lock_guard<std::mutex> lk(g_nearest_mutex);
-      auto it = g_nearest_scratch.find(tree);
-      if (it == g_nearest_scratch.end()) it = g_nearest_scratch.emplace(tree, new NearestScratchHolder()).first;
-      h = it->second;
-      h->sortbuf.ctx = ctx;
-    }
+    NearestScratchHolder *h = &tree->scratch.get<NearestScratchHolder>(&g_nearest_tag);
+    h->sortbuf.ctx = ctx;
     nearest_query(tree, &h->sortbuf, queries, n_queries, idx_out, dist_out, h->idx, h->dist);
   });
 }
@@ -484,6 +479,7 @@ rrtqx_status rrtqx_spheres_upload(rrtqx_spheres *s, const double *centers, const
     s->rec.ensure((size_t)n + 1, st);
     s->active.ensure((size_t)n + 1, st);
     s->n = n;
+    s->version = next_content_stamp();
     if (n == 0) return;
     const double *dc = to_device(ctx, centers, (size_t)n * 3, ctx->stage_f64);
     const double *dr = to_device(ctx, radii, (size_t)n, ctx->stage_f64b);
@@ -503,6 +499,7 @@ rrtqx_status rrtqx_spheres_update(rrtqx_spheres *s, int64_t first, int64_t count
     bind_device(ctx);
     RQ_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "obstacle range out of bounds");
     if (count == 0) return;
+    s->version = next_content_stamp();
     cudaStream_t st = ctx->stream;
     if (radii) {
       const double *dr = to_device(ctx, radii, (size_t)count, ctx->stage_f64b);
@@ -531,9 +528,8 @@ rrtqx_status rrtqx_edge_check_batch(rrtqx_tree *tree, const rrtqx_spheres *spher
     RQ_REQUIRE(tree->d == 3, "SimpleEdge checks need a 3-D tree (explicitEdgeCheck3D)");
     RQ_REQUIRE(n_edges >= 0, "n_edges is negative");
     RQ_REQUIRE(n_edges == 0 || (src && dst && collide_out), "NULL array");
-    if (n_edges && !is_device_ptr(src))
-      for (int64_t e = 0; e < n_edges; ++e)
-        RQ_REQUIRE(src[e] >= 0 && src[e] < tree->n && dst[e] >= 0 && dst[e] < tree->n, "edge endpoint out of range");
+    // endpoint indices are validated on the device, inside the kernels that gather the positions (host and
+    // device arrays alike): a bad index fails the call with RRTQX_ERR_INVALID
     edge_check(ctx, tree, spheres, src, dst, nullptr, nullptr, n_edges, robot_radius, flags, collide_out);
   });
 }

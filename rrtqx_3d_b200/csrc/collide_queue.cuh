@@ -39,6 +39,7 @@ struct SphCoverBufs {
   DevBuf<uint2> pairs;                  // (item, obstacle) pairs that survived the reject
   DevBuf<unsigned> slow;                // items decided by the slow kernels (list A, then list B)
   DevBuf<unsigned long long> n_pairs;   // [0] pairs, [1] slow list A, [2] slow list B
+  uint64_t build_id = 0;                // renewed by every build_sphere_cover: who built the lists last
 };
 
 // One warp per binned obstacle: append it to every cover cell it belongs to (fixed-capacity lists, so one pass,
@@ -95,6 +96,7 @@ constexpr int COV_MAX_OBSTACLES = 65536;  // obstacle numbers are packed into 16
 static inline void build_sphere_cover(rrtqx_ctx *ctx, SphCoverBufs &B, const double4 *rec2, const double2 *thr2,
                                       const float4 *frec2, const int32_t *cstart, SphGrid *dG, int n_upper) {
   cudaStream_t st = ctx->stream;
+  B.build_id = next_content_stamp();
   B.cnt.ensure(COV_CELLS + 1, st);
   B.list_f.ensure((size_t)COV_CELLS * COV_CAPC, st);
   RQ_CUDA(cudaMemsetAsync(B.cnt.p, 0, (COV_CELLS + 1) * sizeof(int32_t), st));
@@ -103,22 +105,20 @@ static inline void build_sphere_cover(rrtqx_ctx *ctx, SphCoverBufs &B, const dou
   post_launch(ctx, 1);
 }
 
-static inline SphCoverBufs &cover_bufs(rrtqx_ctx *ctx) {
-  static std::map<rrtqx_ctx *, SphCoverBufs *> m;  // per context and translation unit, leaked at exit by design
-  auto it = m.find(ctx);
-  if (it == m.end()) it = m.emplace(ctx, new SphCoverBufs()).first;
-  return *it->second;
+inline char g_cover_tag = 0;  // one key for all translation units (C++17 inline variable)
+static inline SphCoverBufs &cover_bufs(rrtqx_ctx *ctx) {  // owned by the context, freed in rrtqx_ctx_destroy
+  return ctx->scratch.get<SphCoverBufs>(&g_cover_tag);
 }
 
 // Batches below the threshold keep the thread-per-edge kernels: the cover build and the extra launches cost
 // ~40 us, the two-stage path saves ~19 ns per 1000 edges in the batch check (break-even ~2e6 edges) and ~44 ns
-// per 1000 items in the add sweep (break-even ~1e6).  Read on every call so that tests can switch paths:
-// RRTQX_EDGE_NO_QUEUE=1 forces the thread-per-edge kernels, RRTQX_COVER_MIN_ITEMS=n moves the threshold.
+// per 1000 items in the add sweep (break-even ~1e6).  The context's tuning (environment read at rrtqx_ctx_create /
+// rrtqx_ctx_reload_tuning) can switch paths: RRTQX_EDGE_NO_QUEUE=1 forces the thread-per-edge kernels,
+// RRTQX_COVER_MIN_ITEMS=n moves the threshold.
 constexpr int64_t PQ_MIN_ITEMS_BATCH = (int64_t)1 << 21, PQ_MIN_ITEMS_SWEEP = (int64_t)1 << 20;
-static inline int64_t cover_min_items(int64_t dflt) {
-  if (getenv("RRTQX_EDGE_NO_QUEUE")) return INT64_MAX;
-  const char *e = getenv("RRTQX_COVER_MIN_ITEMS");
-  return e ? (int64_t)atoll(e) : dflt;
+static inline int64_t cover_min_items(const rrtqx_ctx *ctx, int64_t dflt) {
+  if (ctx->tune.edge_no_queue) return INT64_MAX;
+  return ctx->tune.cover_min_items >= 0 ? ctx->tune.cover_min_items : dflt;
 }
 
 // ---------------------------------------------------------------- pair queue

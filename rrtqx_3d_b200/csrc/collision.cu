@@ -60,14 +60,19 @@ struct SphereTableBufs {
   DevBuf<int32_t> id;
   DevBuf<int32_t> n;
   DevBuf<int32_t> cstart;
+  DevBuf<int32_t> bad;         // device counter of out-of-range edge endpoints
   DevBuf<unsigned char> grid;  // SphGrid header
+  // what the buffers currently hold: the table of obstacle set `key_version` for (robot radius, ignore flag);
+  // grid_level 0: table only, 1: + obstacle grid, 2: + cover lists (build `cover_id` of the context's cover
+  // buffers).  An unchanged obstacle set is not re-binned on every call (the planner checks thousands of edge
+  // batches between two obstacle events).
+  uint64_t key_version = 0, key_rho = 0, cover_id = 0;
+  int key_ignore = -1, grid_level = 0;
 };
 
-static SphereTableBufs &table_bufs(rrtqx_ctx *ctx) {
-  static std::map<rrtqx_ctx *, SphereTableBufs *> m;  // per context, leaked at exit by design
-  auto it = m.find(ctx);
-  if (it == m.end()) it = m.emplace(ctx, new SphereTableBufs()).first;
-  return *it->second;
+static SphereTableBufs &table_bufs(rrtqx_ctx *ctx) {  // owned by the context, freed in rrtqx_ctx_destroy
+  static const char tag = 0;
+  return ctx->scratch.get<SphereTableBufs>(&tag);
 }
 
 // Builds the table on the stream; returns it with n = upper bound (all
@@ -81,9 +86,14 @@ SphereTable build_sphere_table(rrtqx_ctx *ctx, const rrtqx_spheres *s, double ro
   b.thr.ensure(n + 1, st);
   b.id.ensure(n + 1, st);
   b.n.ensure(4, st);
-  sphere_table_kernel<<<1, 1024, 0, st>>>(s->rec.p, s->active.p, (int)n, (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
-                                          robot_radius, b.rec.p, b.thr.p, b.id.p, b.n.p);
-  post_launch(ctx);
+  const int ignore = (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0;
+  uint64_t rho_bits;
+  memcpy(&rho_bits, &robot_radius, sizeof(rho_bits));
+  if (!(s->version != 0 && b.key_version == s->version && b.key_rho == rho_bits && b.key_ignore == ignore)) {
+    sphere_table_kernel<<<1, 1024, 0, st>>>(s->rec.p, s->active.p, (int)n, ignore, robot_radius, b.rec.p, b.thr.p, b.id.p, b.n.p);
+    post_launch(ctx);
+    b.key_version = s->version; b.key_rho = rho_bits; b.key_ignore = ignore; b.grid_level = 0;
+  }
   SphereTable t;
   t.rec = b.rec.p;
   t.thr = b.thr.p;
@@ -99,7 +109,8 @@ __global__ void __launch_bounds__(256)
 edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                        const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
                        const double4 *__restrict__ rec, const double2 *__restrict__ thr, const float4 *__restrict__ frec,
-                       const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ out) {
+                       const int32_t *__restrict__ cstart, const SphGrid *__restrict__ Gp, uint8_t *__restrict__ out,
+                       int n_nodes, int32_t *__restrict__ bad) {
   __shared__ SphGrid G;
   if (threadIdx.x == 0) G = *Gp;
   __syncthreads();
@@ -107,7 +118,13 @@ edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restric
   if (e >= n_edges) return;
   SegPre pre;
   if (SRC_TREE) {
-    const double4 a = pos[src[e]], b = pos[dst[e]];
+    const int ia = src[e], ib = dst[e];
+    if ((unsigned)ia >= (unsigned)n_nodes || (unsigned)ib >= (unsigned)n_nodes) {  // reported as RRTQX_ERR_INVALID
+      atomicAdd(bad, 1);
+      out[e] = 0;
+      return;
+    }
+    const double4 a = pos[ia], b = pos[ib];
     pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
   } else {
     const double *a = starts + 3 * e, *b = ends + 3 * e;
@@ -147,10 +164,18 @@ struct BatchEdgeSrc {
   const int32_t *src, *dst;
   const double *starts, *ends;
   uint8_t *out;
+  int n_nodes;
+  int32_t *bad;  // count of edges with an endpoint outside [0, n_nodes): the call fails with RRTQX_ERR_INVALID
   __device__ __forceinline__ bool endpoints(int64_t i, double a[3], double b[3], int &v) const {
     v = 0;
     if (SRC_TREE) {
-      const double4 pa = pos[src[i]], pb = pos[dst[i]];
+      const int ia = src[i], ib = dst[i];
+      if ((unsigned)ia >= (unsigned)n_nodes || (unsigned)ib >= (unsigned)n_nodes) {
+        atomicAdd(bad, 1);
+        out[i] = 0;
+        return false;
+      }
+      const double4 pa = pos[ia], pb = pos[ib];
       a[0] = pa.x; a[1] = pa.y; a[2] = pa.z;
       b[0] = pb.x; b[1] = pb.y; b[2] = pb.z;
     } else {
@@ -174,7 +199,8 @@ template <bool FMA_DOT, bool SRC_TREE>
 __global__ void __launch_bounds__(256)
 edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
                   const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
-                  SphereTable tab, const int32_t *__restrict__ n_live, uint8_t *__restrict__ out) {
+                  SphereTable tab, const int32_t *__restrict__ n_live, uint8_t *__restrict__ out, int n_nodes,
+                  int32_t *__restrict__ bad) {
   __shared__ double4 s_rec[SPH_TILE];
   __shared__ double2 s_thr[SPH_TILE];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,8 +209,15 @@ edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ s
   bool valid = e < n_edges;
   if (valid) {
     if (SRC_TREE) {
-      double4 a = pos[src[e]], b = pos[dst[e]];
-      pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+      const int ia = src[e], ib = dst[e];
+      if ((unsigned)ia >= (unsigned)n_nodes || (unsigned)ib >= (unsigned)n_nodes) {  // reported as RRTQX_ERR_INVALID
+        atomicAdd(bad, 1);
+        out[e] = 0;
+        valid = false;
+      } else {
+        const double4 a = pos[ia], b = pos[ib];
+        pre = seg_prepare(a.x, a.y, a.z, b.x, b.y, b.z);
+      }
     } else {
       const double *a = starts + 3 * e, *b = ends + 3 * e;
       pre = seg_prepare(a[0], a[1], a[2], b[0], b[1], b[2]);
@@ -228,6 +261,13 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
   const bool out_dev = is_device_ptr(collide_out);
   uint8_t *dout = collide_out;
   if (!out_dev) { ctx->stage_u8.ensure((size_t)n_edges, st); dout = ctx->stage_u8.p; }
+  // endpoint indices are validated on the device (host arrays were already checked by the caller, device arrays
+  // cannot be): a bad index never reaches the position gather, it is counted and the call fails
+  SphereTableBufs &tb = table_bufs(ctx);
+  tb.bad.ensure(4, st);
+  int32_t *dbad = tb.bad.p;
+  const int n_nodes = from_tree ? (int)tree->n : 0;
+  if (from_tree) RQ_CUDA(cudaMemsetAsync(dbad, 0, sizeof(int32_t), st));
   {
     PhaseScope ph(ctx, "edge_check");
     const int32_t *n_live = nullptr;
@@ -236,7 +276,7 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
     const unsigned blocks = (unsigned)div_up(n_edges, TB);
     const double4 *pos = from_tree ? tree->pos.p : nullptr;
     const bool fma = flags & RRTQX_CHECK_FMA_DOT;
-    if (n_edges >= 4096 && spheres->n >= 16 && !getenv("RRTQX_EDGE_NO_GRID")) {
+    if (n_edges >= 4096 && spheres->n >= 16 && !ctx->tune.edge_no_grid) {
       // large batch: bin the obstacles once, then each edge meets only the obstacles around it
       SphereTableBufs &b = table_bufs(ctx);
       b.rec2.ensure((size_t)spheres->n + 1, st);
@@ -245,41 +285,54 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
       b.cstart.ensure(SG_MAX_CELLS + 4, st);
       b.grid.ensure(sizeof(SphGrid) + 16, st);
       SphGrid *dG = (SphGrid *)b.grid.p;
-      const bool use_queue = n_edges >= cover_min_items(PQ_MIN_ITEMS_BATCH) && n_edges < ((int64_t)1 << 32);
-      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, (use_queue && spheres->n <= COV_MAX_OBSTACLES) ? 1 : 0);
+      const bool use_queue = n_edges >= cover_min_items(ctx, PQ_MIN_ITEMS_BATCH) && n_edges < ((int64_t)1 << 32);
+      const bool want_cover = use_queue && spheres->n <= COV_MAX_OBSTACLES;
+      const int want_level = want_cover ? 2 : 1;
+      const bool cached = b.grid_level == want_level && (!want_cover || cover_bufs(ctx).build_id == b.cover_id);
+      if (!cached) {
+        sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, want_cover ? 1 : 0);
+        post_launch(ctx);
+        b.grid_level = want_level;
+      }
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);
-        if (spheres->n <= COV_MAX_OBSTACLES) build_sphere_cover(ctx, cv, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, (int)spheres->n);
+        if (want_cover && !cached) {
+          build_sphere_cover(ctx, cv, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, (int)spheres->n);
+          b.cover_id = cv.build_id;
+        }
         if (from_tree) {
-          BatchEdgeSrc<true> S{pos, dsrc, ddst, nullptr, nullptr, dout};
+          BatchEdgeSrc<true> S{pos, dsrc, ddst, nullptr, nullptr, dout, n_nodes, dbad};
           if (fma) pq_launch<true>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
           else     pq_launch<false>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
         } else {
-          BatchEdgeSrc<false> S{nullptr, nullptr, nullptr, dstarts, dends, dout};
+          BatchEdgeSrc<false> S{nullptr, nullptr, nullptr, dstarts, dends, dout, 0, dbad};
           if (fma) pq_launch<true>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
           else     pq_launch<false>(ctx, cv, S, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
         }
       } else
       if (from_tree) {
-        if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
-        else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
+        if (fma) edge_check_grid_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout, n_nodes, dbad);
+        else     edge_check_grid_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout, n_nodes, dbad);
       } else {
-        if (fma) edge_check_grid_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
-        else     edge_check_grid_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout);
+        if (fma) edge_check_grid_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout, n_nodes, dbad);
+        else     edge_check_grid_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, dout, n_nodes, dbad);
       }
-      post_launch(ctx, 2);
+      post_launch(ctx, use_queue ? 0 : 1);  // pq_launch counts its own kernels
     } else if (from_tree) {
-      if (fma) edge_check_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
-      else     edge_check_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout);
+      if (fma) edge_check_kernel<true, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout, n_nodes, dbad);
+      else     edge_check_kernel<false, true><<<blocks, TB, 0, st>>>(pos, dsrc, ddst, nullptr, nullptr, n_edges, tab, n_live, dout, n_nodes, dbad);
       post_launch(ctx);
     } else {
-      if (fma) edge_check_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
-      else     edge_check_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout);
+      if (fma) edge_check_kernel<true, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout, n_nodes, dbad);
+      else     edge_check_kernel<false, false><<<blocks, TB, 0, st>>>(pos, nullptr, nullptr, dstarts, dends, n_edges, tab, n_live, dout, n_nodes, dbad);
       post_launch(ctx);
     }
   }
   if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n_edges);
+  int32_t n_bad = 0;
+  if (from_tree) RQ_CUDA(cudaMemcpyAsync(&n_bad, dbad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RQ_CUDA(cudaStreamSynchronize(st));
+  RQ_REQUIRE(n_bad == 0, "edge endpoint out of range");
 }
 
 // explicitPointCheck (DRRT_Q.jl:1520-1556) / explicitPointCheck3D (:1558-1590),

@@ -4,9 +4,22 @@
 #pragma once
 #include "common.cuh"
 
+namespace rrtqx {
+// process-wide unique stamps for obstacle-set contents: caches of derived tables (active-obstacle table, obstacle
+// grid, cover lists, the extend_query table) are keyed on the stamp, so an upload / update invalidates them and a
+// new object at a recycled address can never match an old key
+inline uint64_t next_content_stamp() {
+  static std::mutex mu;
+  static uint64_t counter = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  return ++counter;
+}
+}  // namespace rrtqx
+
 struct rrtqx_spheres {
   rrtqx_ctx *ctx = nullptr;
   int64_t n = 0;
+  uint64_t version = 0;  // content stamp, renewed by rrtqx_spheres_upload / rrtqx_spheres_update
   // SoA-in-AoS: (cx, cy, cz, radius) as one 32-byte record + active byte
   rrtqx::DevBuf<double4> rec;
   rrtqx::DevBuf<uint8_t> active;

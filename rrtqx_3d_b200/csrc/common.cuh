@@ -9,7 +9,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,9 +102,72 @@ inline bool is_device_ptr(const void *p) {
 
 }  // namespace rrtqx
 
+// Diagnostic switches.  The environment is read ONCE per context, at rrtqx_ctx_create
+// (and again only on an explicit rrtqx_ctx_reload_tuning): no libc lock or string scan sits inside a planner
+// iteration.  None of the switches selects a CPU path.
+namespace rrtqx {
+struct Tuning {
+  bool edge_no_grid = false, edge_no_queue = false, dubins_check_v1 = false, range_two_pass = false,
+       nearest_warp = false;
+  int64_t cover_min_items = -1;  // < 0: the measured break-even defaults
+  int fused_variant = -1;        // < 0: chosen from the expected neighbour count
+  int range_kernel = 5, v5_nw = 24, qsort_s = 3, qsort_f = 1;
+  unsigned v5_unit = 0;          // 0: V5_UNIT
+  double grid_occupancy = 0.0, grid_aspect = 0.0;  // 0: the tree's defaults
+  void load() {
+    *this = Tuning();
+    auto on = [](const char *n) { return getenv(n) != nullptr; };
+    auto geti = [](const char *n, long long d) { const char *e = getenv(n); return e ? atoll(e) : d; };
+    auto getd = [](const char *n) { const char *e = getenv(n); return e ? atof(e) : 0.0; };
+    edge_no_grid = on("RRTQX_EDGE_NO_GRID");
+    edge_no_queue = on("RRTQX_EDGE_NO_QUEUE");
+    dubins_check_v1 = on("RRTQX_DUBINS_CHECK_V1");
+    range_two_pass = on("RRTQX_RANGE_TWO_PASS");
+    nearest_warp = on("RRTQX_NEAREST_WARP");
+    cover_min_items = geti("RRTQX_COVER_MIN_ITEMS", -1);
+    fused_variant = (int)geti("RRTQX_FUSED_VARIANT", -1);
+    range_kernel = (int)geti("RRTQX_RANGE_KERNEL", 5);
+    v5_nw = (int)geti("RRTQX_V5_NW", 24);
+    const long long u = geti("RRTQX_V5_UNIT", 0);
+    v5_unit = (unsigned)(u > 0 ? u : 0);
+    const long long s = geti("RRTQX_QSORT_S", 3), f = geti("RRTQX_QSORT_F", 1);
+    qsort_s = (int)(s < 1 ? 1 : (s > 16 ? 16 : s));
+    qsort_f = (int)(f < 1 ? 1 : (f > 8 ? 8 : f));
+    const double o = getd("RRTQX_GRID_OCCUPANCY"), a = getd("RRTQX_GRID_ASPECT");
+    grid_occupancy = o > 0.0 ? o : 0.0;
+    grid_aspect = a >= 1.0 ? a : 0.0;
+  }
+};
+
+// Scratch objects owned by a context or a tree, keyed by the address of a tag: created on first use, destroyed
+// with their owner (rrtqx_ctx_destroy / rrtqx_tree_destroy), guarded by the owner's mutex.
+struct ScratchMap {
+  struct Slot { void *p; void (*del)(void *); };
+  std::map<const void *, Slot> slots;
+  std::mutex mu;
+  template <class T>
+  T &get(const void *key) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = slots.find(key);
+    if (it == slots.end())
+      it = slots.emplace(key, Slot{new T(), [](void *q) { delete static_cast<T *>(q); }}).first;
+    return *static_cast<T *>(it->second.p);
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &kv : slots) kv.second.del(kv.second.p);
+    slots.clear();
+  }
+  ~ScratchMap() { clear(); }
+};
+}  // namespace rrtqx
+
 // ------------------------------------------------------------------ context
 struct rrtqx_ctx {
   int device = 0;
+  rrtqx::Tuning tune;
+  rrtqx::ScratchMap scratch;                 // per-context scratch buffers of the collision / sweep paths
+  std::set<const void *> smem_attr_done;     // kernels whose dynamic shared memory opt-in is set on THIS device
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 148;

@@ -233,7 +233,20 @@ extend_query_kernel(GridView g, const ExtendParams prm, const double4 *__restric
   }
 }
 
+// Active obstacles compacted into a dense table (order irrelevant: the kernel takes an OR and a minimum over it).
+// The reference's obstacle list only grows (expired agent obstacles stay in it with obstacleUnused = true,
+// rrtqx.jl:462-530), so the 768-entry shared-memory table of the kernel is filled from the ACTIVE ones only.
+__global__ void extend_compact_kernel(const double4 *__restrict__ rec, const uint8_t *__restrict__ active, int n,
+                                      int ignore_active, double4 *__restrict__ out, int32_t *__restrict__ out_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (ignore_active || active[i])) out[atomicAdd(out_n, 1)] = rec[i];
+}
+
 struct ExtendState {   // per tree: mapped pinned result buffers + device scratch
+  DevBuf<double4> act_rec;            // compacted active obstacles of the set last used
+  DevBuf<int32_t> act_n;
+  uint64_t act_version = 0;           // content stamp of that set (rrtqx_spheres::version); 0: none
+  int act_ignore = -1, n_act = 0;
   ExtendHeader *h_hdr = nullptr, *d_hdr = nullptr;     // mapped pinned (host / device views)
   ExtendEntry *h_ent = nullptr, *d_ent_out = nullptr;  // mapped pinned
   DevBuf<ExtendEntry> scratch;
@@ -260,11 +273,9 @@ struct ExtendState {   // per tree: mapped pinned result buffers + device scratc
   }
 };
 
-static std::map<rrtqx_tree *, ExtendState *> g_extend_state;
-
-void extend_state_drop(rrtqx_tree *t) {
-  auto it = g_extend_state.find(t);
-  if (it != g_extend_state.end()) { delete it->second; g_extend_state.erase(it); }
+static ExtendState &extend_state(rrtqx_tree *t) {  // owned by the tree, freed in rrtqx_tree_destroy
+  static const char tag = 0;
+  return t->scratch.get<ExtendState>(&tag);
 }
 
 void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, double range, double robot_radius,
@@ -275,12 +286,27 @@ void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, do
   cudaStream_t st = ctx->stream;
   RQ_REQUIRE(point != nullptr && !is_device_ptr(point), "point must be a host array");
   RQ_REQUIRE(capacity >= 0, "capacity is negative");
-  RQ_REQUIRE(S->n <= EXT_MAX_SPHERES, "extend_query supports at most 768 obstacles; use the batched calls");
   if (t->n == 0) throw Error(RRTQX_ERR_EMPTY_TREE, "extend query on an empty tree");
   tree_prepare_query(t);
-  ExtendState *&es = g_extend_state[t];
-  if (!es) es = new ExtendState();
+  ExtendState *es = &extend_state(t);
   es->ensure(std::max(capacity, 1), st);
+  const int ignore_active = (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0;
+  if (es->act_version != S->version || es->act_ignore != ignore_active) {  // obstacle set changed since the last call
+    es->act_rec.ensure((size_t)S->n + 1, st);
+    es->act_n.ensure(4, st);
+    RQ_CUDA(cudaMemsetAsync(es->act_n.p, 0, sizeof(int32_t), st));
+    if (S->n > 0) {
+      extend_compact_kernel<<<div_up(S->n, 256), 256, 0, st>>>(S->rec.p, S->active.p, (int)S->n, ignore_active, es->act_rec.p, es->act_n.p);
+      post_launch(ctx);
+    }
+    int32_t na = 0;
+    RQ_CUDA(cudaMemcpyAsync(&na, es->act_n.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+    es->n_act = na;
+    es->act_version = S->version;
+    es->act_ignore = ignore_active;
+  }
+  RQ_REQUIRE(es->n_act <= EXT_MAX_SPHERES, "extend_query supports at most 768 ACTIVE obstacles; use the batched calls");
   ExtendParams prm;
   for (int c = 0; c < 4; ++c) prm.p[c] = c < t->d ? point[c] : 0.0;
   prm.r = range;
@@ -288,14 +314,14 @@ void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, do
   prm.rho = robot_radius;
   prm.capacity = capacity;
   prm.quick_pass = (flags & RRTQX_CHECK_QUICK_PASS) ? 1 : 0;
-  prm.ignore_active = (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0;
+  prm.ignore_active = 1;  // the table handed to the kernel holds the active obstacles only
   prm.fma_dot = (flags & RRTQX_CHECK_FMA_DOT) ? 1 : 0;
   prm.seq = ++es->seq;
   GridView g = t->view();
   {
     // no phase events here: two event records would cost more host time than the kernel's launch
 #define RQ_EXT(D_, F_)                                                                                           \
-  extend_query_kernel<D_, F_><<<1, EXT_WARPS * 32, 0, st>>>(g, prm, S->rec.p, S->active.p, (int)S->n, es->d_hdr, \
+  extend_query_kernel<D_, F_><<<1, EXT_WARPS * 32, 0, st>>>(g, prm, es->act_rec.p, nullptr, es->n_act, es->d_hdr, \
                                                             es->scratch.p, es->d_ent_out)
     const bool fma = prm.fma_dot;
     switch (t->d) {

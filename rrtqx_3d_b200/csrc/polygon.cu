@@ -97,6 +97,8 @@ segment_check_2d_kernel(PolyView P, int ignore_active, const double *__restrict_
   out[i] = hit ? 1 : 0;
 }
 
+#ifdef RRTQX_LEGACY
+// (legacy A/B build only, make EXTRA=-DRRTQX_LEGACY + RRTQX_DUBINS_CHECK_V1=1)
 // Dubins explicitEdgeCheck OR-ed over all obstacles: one warp per edge.  Lanes run the coarse
 // start->end test (radius rho + 2 r_turn) over 32 obstacles at a time; each surviving obstacle
 // is then tested against the trajectory segments, 32 segments per trip.
@@ -129,6 +131,7 @@ dubins_check_v1_kernel(PolyView P, int ignore_active, const double *__restrict__
   }
   if (lane == 0) out[e] = collide ? 1 : 0;
 }
+#endif  // RRTQX_LEGACY
 
 // Same check, coarse stage restructured.  In the first form every lane ran the whole coarse test of its
 // obstacle, so the few obstacles that pass the bounding-circle part made the warp wait through their polygon
@@ -343,10 +346,12 @@ rrtqx_status rrtqx_dubins_edge_check_batch(rrtqx_polygons *p, const double *star
       PhaseScope ph(ctx, "dubins_check");
       // S.robotRadius + 2*S.minTurningRadius (DRRT_DubinsEdge_functions.jl:758)
       const double rho_coarse = robot_radius + 2 * min_turn_radius;
-      if (getenv("RRTQX_DUBINS_CHECK_V1"))
+#ifdef RRTQX_LEGACY
+      if (ctx->tune.dubins_check_v1)
         dubins_check_v1_kernel<<<div_up(n_edges * 32, 256), 256, 0, st>>>(p->view(), (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
                                                                          ds, de, dp, dt, n_edges, robot_radius, rho_coarse, dout);
       else
+#endif
         dubins_check_kernel<<<div_up(n_edges * 32, 256), 256, 0, st>>>(p->view(), (flags & RRTQX_CHECK_IGNORE_ACTIVE) ? 1 : 0,
                                                                       ds, de, dp, dt, n_edges, robot_radius, rho_coarse, dout);
       post_launch(ctx);

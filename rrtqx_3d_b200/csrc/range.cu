@@ -71,8 +71,7 @@ static void sort_queries(rrtqx_tree *t, rrtqx_range_result *r, const double *dq,
   cudaStream_t st = ctx->stream;
   const int TB = 256;
   r->qorder.ensure((size_t)nq, st);
-  static int S = [] { const char *e = getenv("RRTQX_QSORT_S"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
-  static int F = [] { const char *e = getenv("RRTQX_QSORT_F"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  const int S = ctx->tune.qsort_s, F = ctx->tune.qsort_f;
   const int nsx = (t->nx + S - 1) / S, nsy = (t->ny + S - 1) / S, nsz = (t->nz + S - 1) / S;
   const int64_t nbins = (int64_t)nsx * nsy * nsz * S * S * S * F * F * F;
   r->qbins = 0;
@@ -348,7 +347,7 @@ static void range_query_impl(rrtqx_tree *t, const double *queries, int64_t nq, d
   // r <= period / 2: see ghost_expand_kernel); everything else takes the two-pass kernel with explicit dedup
   const bool ghost_ok = t->wrap.num_wraps == 1 && !ranges && std::isfinite(r) && r > 0.0 &&
                         r <= 0.5 * t->wrap.wrap_points[0] && nq < ((int64_t)1 << 29);
-  if ((t->wrap.num_wraps == 0 || ghost_ok) && !getenv("RRTQX_RANGE_TWO_PASS") && t->n_sorted < ((int64_t)1 << 27)) {
+  if ((t->wrap.num_wraps == 0 || ghost_ok) && !ctx->tune.range_two_pass && t->n_sorted < ((int64_t)1 << 27)) {
     range_query_fused<D>(t, dq, dr, nq, r, flags, res);
     return;
   }
@@ -622,7 +621,7 @@ static void nearest_impl(rrtqx_tree *t, rrtqx_range_result *sortbuf, const doubl
   if (dist_out && !dist_dev) { dist_stage.ensure((size_t)nq, st); ddist = dist_stage.p; }
   {
     // large batches over a tree without wrap-around: index the tail first, then one thread per query
-    const bool tpq = t->wrap.num_wraps == 0 && nq >= 4096 && !getenv("RRTQX_NEAREST_WARP");
+    const bool tpq = t->wrap.num_wraps == 0 && nq >= 4096 && !ctx->tune.nearest_warp;
     if (tpq && t->n_sorted < t->n) tree_reindex(t);
     PhaseScope ph(ctx, "nearest");
     sort_queries<D>(t, sortbuf, dq, nq);

@@ -42,6 +42,7 @@ __device__ __forceinline__ unsigned pin_reg(unsigned v) {
   return r;
 }
 
+#ifdef RRTQX_LEGACY
 template <int D, int QN>
 struct Group {
   double q[QN][D];
@@ -52,6 +53,8 @@ struct Group {
   int qid[QN];
   bool live[QN];    // query exists and r > 0
 };
+
+#endif
 
 struct FGrid {
   float inv[3], cell[3];
@@ -96,6 +99,7 @@ __device__ __forceinline__ bool row_cells(const GridView &g, const FGrid &fg, co
 }
 
 // candidate record of sorted slot j
+#ifdef RRTQX_LEGACY  // previous generation of the fused kernel (A/B: make EXTRA=-DRRTQX_LEGACY, RRTQX_RANGE_KERNEL=4)
 template <int D>
 struct Cand {
   double x, y, z, w;
@@ -395,6 +399,8 @@ range_fused_kernel(GridView g, const double *__restrict__ queries, const double 
   }
 }
 
+#endif  // RRTQX_LEGACY
+
 __global__ void thresh_kernel(const double *__restrict__ ranges, int64_t n, double *__restrict__ Tq) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) Tq[i] = sqrt_thresh_lt(ranges[i]);
@@ -417,6 +423,7 @@ static double host_sqrt_thresh_lt(double r) {
 
 #include "range_v5.cuh"
 
+#ifdef RRTQX_LEGACY
 // Kernel variants: more warps per SM when the expected neighbour count is small, bigger hit buffers
 // (fewer warps) when it is large.  Shared memory per block = NW * (2*CAP + FUSED_TAB) * 4 bytes.
 template <int D, int NW, int CAP>
@@ -426,11 +433,8 @@ static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, co
                          int write_lists) {
   constexpr int QN = 2;
   const size_t smem = (size_t)NW * (QN * CAP + FUSED_TAB) * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (ctx->smem_attr_done.insert((const void *)range_fused_kernel<D, QN, NW, CAP>).second)
     RQ_CUDA(cudaFuncSetAttribute(range_fused_kernel<D, QN, NW, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   constexpr int CHUNK = NW * QN * FUSED_ROUNDS;
   const int64_t n_chunks = (nq + CHUNK - 1) / CHUNK;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)ctx->sm_count));
@@ -438,6 +442,8 @@ static void launch_fused(rrtqx_ctx *ctx, const GridView &g, const double *dq, co
                                                                              offsets, idx, dist, cap, cursor, write_lists);
   post_launch(ctx);
 }
+
+#endif  // RRTQX_LEGACY
 
 template <int D>
 static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr, int64_t nq, double r, uint32_t flags,
@@ -501,37 +507,47 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
     k_est = 0.0;
   }
   int variant = k_est <= 576.0 ? 0 : (k_est <= 1280.0 ? 1 : (k_est <= 2048.0 ? 2 : 3));
-  if (const char *e = getenv("RRTQX_FUSED_VARIANT")) variant = atoi(e);
-  static const int kernel_gen = [] { const char *e = getenv("RRTQX_RANGE_KERNEL"); return e ? atoi(e) : 5; }();
+  if (ctx->tune.fused_variant >= 0) variant = ctx->tune.fused_variant;
+#ifdef RRTQX_LEGACY
+  const int kernel_gen = ctx->tune.range_kernel;
+#endif
   unsigned long long total = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     GridView g = t->view();
     RQ_CUDA(cudaMemsetAsync(res->cursor.p, 0, 4 * sizeof(unsigned long long), st));
     {
       PhaseScope p2(ctx, "range_fill");
+#ifdef RRTQX_LEGACY
 #define RQ_FUSED(NW_, CAP_)                                                                                          \
   launch_fused<D, NW_, CAP_>(ctx, g, dq, res->qbins > 0 ? res->qsorted.p : nullptr, res->qorder.p, nq, r, T, dr, dT, res->counts.p, res->offsets.p, res->idx.p, \
                              want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p,             \
                              count_only ? 0 : 1)
+#endif
 #define RQ_V5(NW_, CAP_, TAB_)                                                                                       \
   launch_v5<D, NW_, CAP_, TAB_>(ctx, g, kq, kqs, korder, knq, r, T, dr, dT, kcounts, koffsets, res->idx.p, \
                                 want_dist ? res->dist.p : nullptr, (unsigned long long)cap, res->cursor.p, count_only ? 0 : 1, ghost ? 1 : 0)
-      if (kernel_gen >= 5 || ghost) {
+#ifdef RRTQX_LEGACY
+      if (kernel_gen >= 5 || ghost)
+#endif
+      {
         // v5 (FP32 filter scan, packed exact records, 16-bit hit codes): hit buffers leave 32*V5_U entries of
         // head-room; the octet table must hold a whole pair's region (else the pair takes the exact routine)
-        static const int v5_nw = [] { const char *e = getenv("RRTQX_V5_NW"); return e ? atoi(e) : 24; }();
+        const int v5_nw = ctx->tune.v5_nw;
         if (variant == 0 && v5_nw == 28) RQ_V5(28, 704, 256);
         else if (variant == 0 && v5_nw == 20) RQ_V5(20, 704, 256);
         else if (variant == 0) RQ_V5(24, 704, 256);     // 24 warps/SM (80 registers), 94 KB shared
         else if (variant == 1) RQ_V5(24, 1408, 512);    // 186 KB
         else if (variant == 2) RQ_V5(16, 2176, 1024);   // 205 KB
         else RQ_V5(8, 4224, 2048);                      // 201 KB
-      } else
+      }
+#ifdef RRTQX_LEGACY
+      else
       if (variant == 0) RQ_FUSED(28, 576);        // 28 warps/SM (72 registers), 158 KB shared; measured best of 20/24/28/32
       else if (variant == 1) RQ_FUSED(20, 1280);  // 20 warps/SM, 225 KB
       else if (variant == 2) RQ_FUSED(12, 2048);  // 12 warps/SM, 209 KB
       else RQ_FUSED(6, 4096);                     //  6 warps/SM, 203 KB: up to 4096 neighbours buffered per query
 #undef RQ_FUSED
+#endif
 #undef RQ_V5
     }
     RQ_CUDA(cudaMemcpyAsync(&total, res->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, st));

@@ -700,18 +700,16 @@ static void launch_v5(rrtqx_ctx *ctx, const GridView &g, const double *dq, const
                       int64_t *offsets, int32_t *idx, double *dist, unsigned long long cap, unsigned long long *cursor,
                       int write_lists, int ghost_pairs = 0) {
   const size_t smem = (size_t)NW * (CAP + TAB + V5_TABPAD) * sizeof(int);  // 16-bit hit codes: 2 * CAP * 2 bytes
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device: tracked per context, not per process
+  if (ctx->smem_attr_done.insert((const void *)range_v5_kernel<D, NW, CAP, TAB, true>).second) {
     RQ_CUDA(cudaFuncSetAttribute(range_v5_kernel<D, NW, CAP, TAB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RQ_CUDA(cudaFuncSetAttribute(range_v5_kernel<D, NW, CAP, TAB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   V5Params P;
   P.RU = v5_radius(r, T, true);
   P.invx = (float)g.inv[0]; P.invy = (float)g.inv[1]; P.invz = (float)g.inv[2];
   P.celly = (float)g.cell[1]; P.cellz = (float)g.cell[2];
-  static const unsigned unit_env = [] { const char *e = getenv("RRTQX_V5_UNIT"); int v = e ? atoi(e) : 0; return (unsigned)(v > 0 ? v : 0); }();
-  P.unit = unit_env ? unit_env : (unsigned)V5_UNIT;
+  P.unit = ctx->tune.v5_unit ? ctx->tune.v5_unit : (unsigned)V5_UNIT;
   P.ghost_pairs = ghost_pairs;
   const int64_t n_units = ((nq + 1) / 2 + P.unit - 1) / P.unit;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)ctx->sm_count));

@@ -94,11 +94,34 @@ void edges_rebuild(rrtqx_edges *E) {
   E->dirty = false;
 }
 
-static void validate_endpoints(const int32_t *src, const int32_t *dst, int64_t ne, int64_t nn) {
-  // indices are validated on the host side only when the arrays are host arrays
-  if (ne && !is_device_ptr(src))
+__global__ void validate_endpoints_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t ne,
+                                          int64_t nn, int32_t *__restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int a = src[e], b = dst[e];
+  if (a < 0 || a >= nn || b < 0 || b >= nn) atomicAdd(bad, 1);
+}
+
+// Host arrays are checked on the host, device arrays by a small kernel: a bad index fails the call with
+// RRTQX_ERR_INVALID before it can reach the histogram atomics or the position gathers.
+static void validate_endpoints(rrtqx_tree *t, const int32_t *src, const int32_t *dst, int64_t ne, int64_t nn) {
+  if (!ne) return;
+  if (!is_device_ptr(src) && !is_device_ptr(dst)) {
     for (int64_t e = 0; e < ne; ++e)
       RQ_REQUIRE(src[e] >= 0 && src[e] < nn && dst[e] >= 0 && dst[e] < nn, "edge endpoint out of range");
+    return;
+  }
+  RQ_REQUIRE(is_device_ptr(src) && is_device_ptr(dst), "src and dst must both be host or both be device arrays");
+  rrtqx_ctx *ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  t->flagbuf.ensure(8, st);
+  RQ_CUDA(cudaMemsetAsync(t->flagbuf.p, 0, sizeof(int32_t), st));
+  validate_endpoints_kernel<<<div_up(ne, 256), 256, 0, st>>>(src, dst, ne, nn, t->flagbuf.p);
+  post_launch(ctx);
+  int32_t bad = 0;
+  RQ_CUDA(cudaMemcpyAsync(&bad, t->flagbuf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RQ_CUDA(cudaStreamSynchronize(st));
+  RQ_REQUIRE(bad == 0, "edge endpoint out of range");
 }
 
 void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
@@ -110,7 +133,7 @@ void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
   RQ_REQUIRE(ne >= 0 && ne < (int64_t)0x7fffffff, "n_edges out of range");
   const int64_t nn = t->n;
   RQ_REQUIRE(parent == nullptr || n_parent == nn, "parent array must have one entry per tree node");
-  validate_endpoints(src, dst, ne, nn);
+  validate_endpoints(t, src, dst, ne, nn);
   E->n_edges = ne;
   E->n_nodes = 0;
   E->has_parent = parent != nullptr;
@@ -138,7 +161,7 @@ void edges_append(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
   RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
   RQ_REQUIRE(n_new >= 0 && E->n_edges + n_new < (int64_t)0x7fffffff, "n_edges out of range");
   if (n_new == 0) return;
-  validate_endpoints(src, dst, n_new, t->n);
+  validate_endpoints(t, src, dst, n_new, t->n);
   const size_t old = (size_t)E->n_edges;
   E->src.ensure(old + (size_t)n_new + 1, st, old);
   E->dst.ensure(old + (size_t)n_new + 1, st, old);
@@ -565,7 +588,7 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       SphGrid *dG = (SphGrid *)R->grid.p;
       R->ob_frec2.ensure((size_t)n_obs + 1, st);
       const int64_t work = E->n_edges + E->n_nodes;
-      const bool use_queue = work >= cover_min_items(PQ_MIN_ITEMS_SWEEP) && work < ((int64_t)1 << 32);
+      const bool use_queue = work >= cover_min_items(ctx, PQ_MIN_ITEMS_SWEEP) && work < ((int64_t)1 << 32);
       sphere_grid_kernel<<<1, 1024, 0, st>>>(R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, R->ob_rec2.p,
                                              R->ob_thr2.p, R->ob_ext2.p, R->cstart.p, dG, R->ob_frec2.p, (use_queue && n_obs <= COV_MAX_OBSTACLES) ? 1 : 0);
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;

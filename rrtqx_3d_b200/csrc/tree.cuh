@@ -66,6 +66,7 @@ struct rrtqx_tree {
   double occupancy = 4.0;
   double aspect = 1.0;   // cell width across rows / cell length along x
   int64_t tail_limit = 4096;
+  rrtqx::ScratchMap scratch;  // per-tree scratch (nearest-query sort buffers, extend_query state)
 
   // node table (insertion order)
   rrtqx::DevBuf<double4> pos;

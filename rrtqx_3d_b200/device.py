@@ -37,6 +37,10 @@ class Context:
     def sync(self):
         A.check(self.L.rrtqx_ctx_sync(self.h), self.h)
 
+    def reload_tuning(self):
+        """Re-read the diagnostic RRTQX_* environment switches (they are otherwise read once, at creation)."""
+        A.check(self.L.rrtqx_ctx_reload_tuning(self.h), self.h)
+
     def kernel_launches(self) -> int:
         n = A.i64(0)
         A.check(self.L.rrtqx_ctx_kernel_launches(self.h, C.byref(n)), self.h)

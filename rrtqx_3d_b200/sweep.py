@@ -95,7 +95,8 @@ def removeObstacle(S: CSpace, KD: KDTree, Q, ob: SphereObstacle, root, hyberBall
     """removeObstacle (DRRT_Q.jl:3295-3362).  qx_semantics=True reproduces the QX fork, which sets
     ob.obstacleUnused = true BEFORE the loop so nothing is ever restored (SURVEY appendix B11);
     False gives the Otte generation (DRRT.jl:3202-3268).  Q may provide
-    recalculateLMCMineVTwo(node, root, r) and verifyInQueue(node)."""
+    recalculateLMCMineVTwo(node, root, r), verifyInQueue(node) and lessQ(a, b) (the key comparison of
+    DRRT_Q.jl:3355; when Q has no lessQ the comparison counts as true)."""
     ctx = KD.ctx
     if edges is None:
         edges = EdgeMirror(KD).rebuild()
@@ -117,7 +118,10 @@ def removeObstacle(S: CSpace, KD: KDTree, Q, ob: SphereObstacle, root, hyberBall
         n = KD.nodes[int(v)]
         if Q is not None and hasattr(Q, "recalculateLMCMineVTwo"):
             Q.recalculateLMCMineVTwo(n, root, hyberBallRad)
-        if Q is not None and hasattr(Q, "verifyInQueue"):
+        # :3354-3356  only nodes that became inconsistent and are relevant to the robot are queued
+        less = getattr(Q, "lessQ", None) if Q is not None else None
+        if (Q is not None and hasattr(Q, "verifyInQueue") and n.rrtTreeCost != n.rrtLMC
+                and (less is None or less(n, moveGoal))):
             Q.verifyInQueue(n)
     ob.obstacleUnused = True                                     # :3361
     return restored, requeue

@@ -103,6 +103,14 @@ class _Queue:
     def verifyInQueue(self, n):
         self.q.append(n)
 
+    # removeObstacle queues a node only if it became inconsistent AND lessQ(node, moveGoal) (DRRT_Q.jl:3352-3357)
+    def recalculateLMCMineVTwo(self, n, root, r):
+        if n.kdIndex % 2 == 0:
+            n.rrtLMC = 1.0          # rrtTreeCost stays Inf: inconsistent
+
+    def lessQ(self, a, b):
+        return a.kdIndex % 3 != 0
+
 
 def test_add_and_remove_obstacle_mutations(ctx):
     pts, _, _ = W.c2_workload(4000, 1)
@@ -171,4 +179,5 @@ def test_add_and_remove_obstacle_mutations(ctx):
             hit_other = bool(Lo.orc_edge_check_sphere(oth, P(n.position), P(e.endNode.position), 0.5, 0))
             hit_ob = n.kdIndex in cand and bool(Lo.orc_edge_check_sphere(one, P(n.position), P(e.endNode.position), 0.5, 0))
             assert (e.dist == math.inf) == (hit_ob and hit_other)
-    assert len(restored) > 0 and {n.kdIndex for n in Q.q} == set(requeue.tolist())
+    want_q = {v for v in requeue.tolist() if v % 2 == 0 and v % 3 != 0}
+    assert len(restored) > 0 and {n.kdIndex for n in Q.q} == want_q and 0 < len(want_q) < len(requeue)

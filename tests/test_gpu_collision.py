@@ -347,6 +347,7 @@ def test_edge_check_cover_lists_short_edges(ctx):
     }
     import os
     os.environ["RRTQX_COVER_MIN_ITEMS"] = "1"   # the two-stage path is the default only above ~2e6 edges
+    ctx.reload_tuning()                         # switches are read at context creation / on request only
     try:
         for name, (c, r) in sets.items():
             c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
@@ -361,6 +362,7 @@ def test_edge_check_cover_lists_short_edges(ctx):
                 assert 0 < got.sum() < len(got)
     finally:
         del os.environ["RRTQX_COVER_MIN_ITEMS"]
+        ctx.reload_tuning()
 
 
 def test_two_stage_and_thread_per_edge_paths_agree(ctx):
@@ -382,6 +384,7 @@ def test_two_stage_and_thread_per_edge_paths_agree(ctx):
     for mode, env in (("default", {}), ("no_queue", {"RRTQX_EDGE_NO_QUEUE": "1"}), ("forced", {"RRTQX_COVER_MIN_ITEMS": "1"})):
         for k, v in env.items():
             os.environ[k] = v
+        ctx.reload_tuning()
         try:
             full = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS)
             part = edge_check_batch(t, S, src[small], dst[small], W.ROBOT_RADIUS)
@@ -390,8 +393,114 @@ def test_two_stage_and_thread_per_edge_paths_agree(ctx):
         finally:
             for k in env:
                 del os.environ[k]
+            ctx.reload_tuning()
     for mode, (full, part, be, on) in results.items():
         assert np.array_equal(full, want), mode
         assert np.array_equal(part, want[small]), mode
         assert np.array_equal(be, results["default"][2]) and np.array_equal(on, results["default"][3]), mode
     assert 0 < want.sum() < len(want) and len(results["default"][2]) > 0
+
+
+def test_bad_edge_endpoints_fail_the_call_host_and_device_arrays(ctx, building2):
+    """An out-of-range endpoint must give RRTQX_ERR_INVALID -- also when src / dst live on the device, where the
+    host cannot look at them (validated inside the gathering kernels / by a small kernel at edge upload)."""
+    import torch
+    centers, radii, _ = building2
+    pts, _, _ = W.c2_workload(6000, 1)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts)
+    S = SphereSet(ctx, centers, radii)
+    src = np.arange(5000, dtype=np.int32)
+    dst = src[::-1].copy()
+    good = edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS)
+    for bad_value in (-1, 6000, 2 ** 31 - 1):
+        for n_e in (100, 5000):           # tiled kernel / obstacle-grid kernel
+            s2, d2 = src[:n_e].copy(), dst[:n_e].copy()
+            d2[n_e // 2] = bad_value
+            with pytest.raises(A.RRTQXError) as ei:
+                edge_check_batch(t, S, s2, d2, W.ROBOT_RADIUS)
+            assert ei.value.status == A.ERR_INVALID
+            ds, dd = torch.from_numpy(s2).cuda(), torch.from_numpy(d2).cuda()
+            out = torch.zeros(n_e, dtype=torch.uint8, device="cuda")
+            with pytest.raises(A.RRTQXError) as ei:
+                edge_check_batch(t, S, ds.data_ptr(), dd.data_ptr(), W.ROBOT_RADIUS, n_edges=n_e, out=out.data_ptr())
+            assert ei.value.status == A.ERR_INVALID
+        E = EdgeSet(t)
+        d2 = dst.copy()
+        d2[17] = bad_value
+        ds, dd = torch.from_numpy(src).cuda(), torch.from_numpy(d2).cuda()
+        with pytest.raises(A.RRTQXError):
+            E.upload(ds.data_ptr(), dd.data_ptr(), None, n_edges=len(src))
+    # the context is still healthy afterwards
+    assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS), good)
+
+
+def test_cached_obstacle_tables_follow_updates(ctx):
+    """The active-obstacle table / obstacle grid / cover lists are cached per obstacle-set content: an in-place
+    update, another robot radius, another flag or another obstacle set must never see stale tables."""
+    pts, _, _ = W.c2_workload(12000, 1)
+    t = DeviceTree(ctx, 3)
+    t.insert_batch(pts)
+    u = W.splitmix64(5, 0, 2 * 20000)
+    src = (u[:20000] % np.uint64(len(pts))).astype(np.int32)
+    dst = ((src.astype(np.int64) + 1 + (u[20000:] % np.uint64(40)).astype(np.int64)) % len(pts)).astype(np.int32)
+    c, r = W.c3_obstacles(64)
+    S = SphereSet(ctx, c, r)
+    S2 = SphereSet(ctx, c[::-1].copy() * 0.5, r[::-1].copy())
+    import os
+    for forced in (False, True):
+        if forced:
+            os.environ["RRTQX_COVER_MIN_ITEMS"] = "1"
+        ctx.reload_tuning()
+        try:
+            act = np.ones(64, np.uint8)
+            for step in range(4):
+                sph, ns = oracle.make_spheres(c, r, unused=1 - act)
+                for rho in (W.ROBOT_RADIUS, 1.25):
+                    for _ in range(2):      # second call: served from the cache
+                        assert np.array_equal(edge_check_batch(t, S, src, dst, rho), _orc_edges(sph, ns, pts, src, dst, rho))
+                sph_all, _ = oracle.make_spheres(c, r)
+                assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_IGNORE_ACTIVE),
+                                      _orc_edges(sph_all, ns, pts, src, dst, W.ROBOT_RADIUS))
+                sph2, ns2 = oracle.make_spheres(c[::-1].copy() * 0.5, r[::-1].copy())
+                assert np.array_equal(edge_check_batch(t, S2, src, dst, W.ROBOT_RADIUS), _orc_edges(sph2, ns2, pts, src, dst, W.ROBOT_RADIUS))
+                act[step * 16:(step + 1) * 16:2] = 0
+                r = r.copy()
+                r[step] += 0.75
+                S.update(0, radii=r, active=act)
+        finally:
+            os.environ.pop("RRTQX_COVER_MIN_ITEMS", None)
+            ctx.reload_tuning()
+
+
+def test_contexts_come_and_go():
+    """Several contexts in one process, created and destroyed in turn: the per-context scratch (obstacle tables,
+    cover lists, pair lists) and the per-context shared-memory opt-in of the range kernel live and die with their
+    context (a recycled address must never meet another context's buffers)."""
+    from rrtqx_3d_b200.device import Context
+    pts, qs, r = W.c2_workload(20000, 3000)
+    c, rad = W.c3_obstacles(32)
+    sph, ns = oracle.make_spheres(c, rad)
+    src = np.arange(10000, dtype=np.int32)
+    dst = (src + 7) % 20000
+    want = _orc_edges(sph, ns, pts, src, dst, W.ROBOT_RADIUS)
+    orc = oracle.KDTree(3)
+    orc.insert_batch(pts)
+    oc, _, _, _ = orc.range_batch(r, qs, want_lists=False, nthreads=8)
+    alive = []
+    for round_ in range(4):
+        cx = Context(0)
+        t = DeviceTree(cx, 3)
+        t.insert_batch(pts)
+        S = SphereSet(cx, c, rad)
+        assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS), want)
+        res, _ = t.range_query(qs, r)
+        counts, _ = res.layout()
+        assert np.array_equal(counts, oc)
+        if round_ % 2 == 0:
+            alive.append((cx, t, S, res))      # keep two contexts alive next to the following ones
+        else:
+            res.close(); S.close(); t.close(); cx.close()
+    for cx, t, S, res in alive:
+        assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS), want)
+        res.close(); S.close(); t.close(); cx.close()

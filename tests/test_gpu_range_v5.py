@@ -74,11 +74,13 @@ def test_forced_small_variant_overflows_table_and_buffers(ctx):
     pts, qs, _ = W.c2_workload(60000, 2100)
     t, orc = _tree(ctx, pts)
     os.environ["RRTQX_FUSED_VARIANT"] = "0"
+    ctx.reload_tuning()
     try:
         for r in (6.5, 9.0):       # ~1100 and ~2900 neighbours per query
             _check(t, orc, qs, r, stride=53)
     finally:
         del os.environ["RRTQX_FUSED_VARIANT"]
+        ctx.reload_tuning()
     _check(t, orc, qs, 6.5, stride=53)   # and through the variant the library picks itself
 
 
