@@ -399,6 +399,62 @@ RRTQX_API rrtqx_status rrtqx_dubins_edge_check_batch(
     double robot_radius, double min_turn_radius, uint32_t flags,
     uint8_t *collide_out);
 
+/* ------------------------------------- Otte / Dubins obstacle sweeps (DRRT.jl) */
+/* addNewObstacle / removeObstacle of the Otte generation with DubinsEdge
+ * (DRRT.jl:3127-3197, 3202-3268; candidates findPointsInConflictWithObstacle
+ * :3048-3122; edge test = Dubins explicitEdgeCheck,
+ * DRRT_DubinsEdge_functions.jl:750-774) over a resident edge set
+ * (rrtqx_edges_upload / _append / _set_parents on a 4-D [x y t theta] tree with
+ * the theta wrap, or a plain 2-D tree).
+ *
+ * The sweeps work on ITEMS: item e < n_edges is out-edge e (upload order),
+ * item n_edges + v is the parent edge of node v (skipped when parent[v] < 0).
+ * Every item needs its trajectory (edge.trajectory[:,1:2]) resident on the
+ * device, as a CSR over the items: traj_ptr[n_edges + n_nodes + 1] (host or
+ * device), traj_xy rows x 2.  Either upload the planner's own trajectories
+ * (bit-exact booleans GIVEN the trajectory points) ...*/
+RRTQX_API rrtqx_status rrtqx_edges_set_trajectories(rrtqx_edges *e,
+                                                    const int64_t *traj_ptr,
+                                                    const double *traj_xy);
+/* ... or have the device solve every item with calculateTrajectory
+ * (DRRT_DubinsEdge_functions.jl:329-709; d == 4): start / end poses are the
+ * resident node positions.  *n_rows_out = total trajectory rows.  Both calls
+ * must be repeated after the edge set, the parents or the tree size change. */
+RRTQX_API rrtqx_status rrtqx_edges_solve_trajectories(rrtqx_edges *e,
+                                                      double min_turn_radius,
+                                                      int64_t *n_rows_out);
+/* device views of the resident trajectories (RRTQX_ERR_STATE when none) */
+RRTQX_API rrtqx_status rrtqx_edges_trajectories_device(
+    const rrtqx_edges *e, const int64_t **traj_ptr, const double **traj_xy,
+    int64_t *n_items, int64_t *n_rows);
+/* copies them out: traj_ptr (n_items + 1) and traj_xy (n_rows x 2), host or
+ * device destinations, either may be NULL */
+RRTQX_API rrtqx_status rrtqx_edges_trajectories_fetch(rrtqx_edges *e,
+                                                      int64_t *traj_ptr,
+                                                      double *traj_xy);
+/* Add sweep for obstacles ob_ids[0..n_obs) of `polygons` (treated as active,
+ * DRRT.jl:3129).  For obstacle o the candidate nodes are
+ *   kdFindWithinRange(KD, ((rho+delta)+radius_o)+pi, [x_o y_o 0.0 pi])  (d == 4)
+ *   kdFindWithinRange(KD,  (rho+delta)+radius_o,     [x_o y_o])         (d == 2)
+ * ghost identities of the wrapped heading included; out-edges of candidates
+ * that collide are "blocked" (:3156-3158), candidates whose parent edge
+ * collides are "orphans" (:3164-3177).  Result as rrtqx_obstacle_add_sweep
+ * (n_candidates / n_pair_tests are reported as -1). */
+RRTQX_API rrtqx_status rrtqx_obstacle_add_sweep_2d(
+    rrtqx_edges *edges, const rrtqx_polygons *polygons, const int32_t *ob_ids,
+    int64_t n_obs, double robot_radius, double delta, double min_turn_radius,
+    uint32_t flags, rrtqx_sweep_result **result);
+/* Remove sweep for ONE obstacle ob_id, Otte semantics (the obstacle is still
+ * active while tested, :3228 vs :3267): a flagged edge (edge_dist_inf[e]) whose
+ * start node is a candidate, that collides with ob_id and with none of
+ * other_ids (the caller evaluates :3238) is "restored"; its start node is
+ * reported for the LMC recompute. */
+RRTQX_API rrtqx_status rrtqx_obstacle_remove_sweep_2d(
+    rrtqx_edges *edges, const rrtqx_polygons *polygons, int32_t ob_id,
+    const int32_t *other_ids, int64_t n_others, const uint8_t *edge_dist_inf,
+    double robot_radius, double delta, double min_turn_radius, uint32_t flags,
+    rrtqx_sweep_result **result);
+
 /* ------------------------------------------------ Dubins solver on the device */
 /* calculateTrajectory(S, edge::DubinsEdge), space without time
  * (DRRT_DubinsEdge_functions.jl:329-709; rightTurnDist / leftTurnDist

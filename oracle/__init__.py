@@ -98,6 +98,11 @@ def lib() -> C.CDLL:
         "orc_polygon_bound": (None, [c_f64p, i32, c_f64p, c_f64p, c_f64p]),
         "orc_edge_check_2d": (cint, [C.POINTER(Obstacle2D), c_f64p, c_f64p, f64]),
         "orc_edge_check_dubins": (cint, [C.POINTER(Obstacle2D), c_f64p, c_f64p, c_f64p, i32, f64, f64]),
+        "orc_obstacle_add_sweep_2d": (cint, [vp, C.POINTER(Obstacle2D), cint, f64, f64, f64, c_i64p, c_i32p, c_i32p,
+                                             c_i64p, c_f64p, c_i32p, c_i64p, i64, c_i32p, c_i64p, i64, c_i64p, c_i64p]),
+        "orc_obstacle_remove_sweep_2d": (cint, [vp, C.POINTER(Obstacle2D), cint, C.POINTER(Obstacle2D), i64, f64, f64,
+                                                f64, c_i64p, c_i32p, c_i64p, c_f64p, c_u8p, c_i32p, c_i64p, i64,
+                                                c_i32p, c_i64p, i64]),
         "orc_dubins_trajectory": (cint, [c_f64p, c_f64p, f64, c_f64p, c_i32p, c_f64p, i32]),
         "orc_saturate_dubins": (None, [c_f64p, c_f64p, f64]),
     }

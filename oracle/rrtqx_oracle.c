@@ -1064,6 +1064,123 @@ int orc_edge_check_dubins(const orc_obstacle2d *ob, const double *start_pos,
   return 0;
 }
 
+/* ------------------------------- Otte / Dubins obstacle sweeps (DRRT.jl) */
+
+/* findPointsInConflictWithObstacle, Otte generation (DRRT.jl:3048-3122), obstacle kinds 1-5, space without time:
+ *   no theta:  searchRange = (rho + delta) + ob.radius            about ob.position (1x2)            :3058-3059
+ *   theta   :  searchRange = ((rho + delta) + ob.radius) + pi     about [ob.x ob.y 0.0 pi]          :3061-3064
+ * through kdFindWithinRange (ghost identities of the wrapped theta included). */
+static int64_t conflict_candidates_2d(const orc_kdtree *t, const orc_obstacle2d *ob, int has_theta,
+                                      double robot_radius, double delta, uint8_t *marks, int32_t **idx_out) {
+  double search_range = (robot_radius + delta) + ob->radius;
+  double q[ORC_MAX_D] = {ob->pos[0], ob->pos[1], 0.0, 0.0};
+  if (has_theta) {
+    search_range = search_range + 3.141592653589793;
+    q[3] = 3.141592653589793;
+  }
+  int64_t cap = t->n ? t->n : 1;
+  int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * cap);
+  int64_t len = orc_kd_find_within_range(t, search_range, q, marks, idx, NULL, cap, 0);
+  *idx_out = idx;
+  return len;
+}
+
+/* Dubins explicitEdgeCheck of CSR item i (start node -> end node, trajectory rows traj_ptr[i]..traj_ptr[i+1]) */
+static int dubins_item_check(const orc_kdtree *t, const orc_obstacle2d *ob, int32_t start, int32_t end,
+                             const int64_t *traj_ptr, const double *traj_xy, int64_t item, double robot_radius,
+                             double min_turn_radius) {
+  return orc_edge_check_dubins(ob, POS(t, start), POS(t, end), traj_xy + 2 * traj_ptr[item],
+                               (int32_t)(traj_ptr[item + 1] - traj_ptr[item]), robot_radius, min_turn_radius);
+}
+
+/* addNewObstacle, Otte generation with DubinsEdge (DRRT.jl:3127-3197) */
+int orc_obstacle_add_sweep_2d(const orc_kdtree *t, const orc_obstacle2d *ob_in, int has_theta, double robot_radius,
+                              double delta, double min_turn_radius, const int64_t *row_ptr, const int32_t *col,
+                              const int32_t *parent, const int64_t *traj_ptr, const double *traj_xy,
+                              int32_t *blocked_edges, int64_t *n_blocked, int64_t cap_blocked, int32_t *orphans,
+                              int64_t *n_orphans, int64_t cap_orphans, int64_t *n_candidates,
+                              int64_t *n_edge_tests) {
+  orc_obstacle2d ob = *ob_in;
+  ob.unused = 0; /* :3129 ob.obstacleUnused = false */
+  const int64_t n_edges = row_ptr[t->n];
+  uint8_t *marks = (uint8_t *)calloc(t->n ? t->n : 1, 1);
+  int32_t *cand = NULL;
+  int64_t nc = conflict_candidates_2d(t, &ob, has_theta, robot_radius, delta, marks, &cand);
+  int64_t nb = 0, no = 0, ntests = 0;
+  int rc = 0;
+  for (int64_t k = nc - 1; k >= 0; --k) { /* popFromRangeList: last pushed first (:3141-3142) */
+    int32_t node = cand[k];
+    for (int64_t e = row_ptr[node]; e < row_ptr[node + 1]; ++e) { /* :3148-3160 */
+      ntests += 1;
+      if (dubins_item_check(t, &ob, node, col[e], traj_ptr, traj_xy, e, robot_radius, min_turn_radius)) {
+        if (nb < cap_blocked) blocked_edges[nb] = (int32_t)e; else rc = -1;
+        nb += 1;
+      }
+    }
+    if (parent && parent[node] >= 0) { /* :3164-3177 */
+      ntests += 1;
+      if (dubins_item_check(t, &ob, node, parent[node], traj_ptr, traj_xy, n_edges + node, robot_radius,
+                            min_turn_radius)) {
+        if (no < cap_orphans) orphans[no] = node; else rc = -1;
+        no += 1;
+      }
+    }
+  }
+  free(cand);
+  free(marks);
+  *n_blocked = nb;
+  *n_orphans = no;
+  if (n_candidates) *n_candidates = nc;
+  if (n_edge_tests) *n_edge_tests = ntests;
+  return rc;
+}
+
+/* removeObstacle, Otte generation with DubinsEdge (DRRT.jl:3202-3268): the removed obstacle is still active while
+ * it is tested (obstacleUnused is set at the very end, :3267); `others` = the obstacles that pass the caller's
+ * evaluation of :3238 (obOther != ob && !obstacleUnused && startTime <= timeElapsed <= startTime + lifeSpan). */
+int orc_obstacle_remove_sweep_2d(const orc_kdtree *t, const orc_obstacle2d *ob, int has_theta,
+                                 const orc_obstacle2d *others, int64_t n_others, double robot_radius, double delta,
+                                 double min_turn_radius, const int64_t *row_ptr, const int32_t *col,
+                                 const int64_t *traj_ptr, const double *traj_xy, const uint8_t *edge_dist_inf,
+                                 int32_t *restored_edges, int64_t *n_restored, int64_t cap_restored,
+                                 int32_t *requeue_nodes, int64_t *n_requeue, int64_t cap_requeue) {
+  uint8_t *marks = (uint8_t *)calloc(t->n ? t->n : 1, 1);
+  int32_t *cand = NULL;
+  int64_t nc = conflict_candidates_2d(t, ob, has_theta, robot_radius, delta, marks, &cand);
+  int64_t nr = 0, nq = 0;
+  int rc = 0;
+  for (int64_t k = nc - 1; k >= 0; --k) {
+    int32_t node = cand[k];
+    int neighbors_were_blocked = 0;
+    for (int64_t e = row_ptr[node]; e < row_ptr[node + 1]; ++e) {
+      if (edge_dist_inf[e] &&
+          dubins_item_check(t, ob, node, col[e], traj_ptr, traj_xy, e, robot_radius, min_turn_radius)) { /* :3228 */
+        int conflicts = 0;
+        for (int64_t o = 0; o < n_others; ++o) { /* :3234-3246 */
+          if (dubins_item_check(t, &others[o], node, col[e], traj_ptr, traj_xy, e, robot_radius, min_turn_radius)) {
+            conflicts = 1;
+            break;
+          }
+        }
+        if (!conflicts) { /* :3249-3255 */
+          if (nr < cap_restored) restored_edges[nr] = (int32_t)e; else rc = -1;
+          nr += 1;
+          neighbors_were_blocked = 1;
+        }
+      }
+    }
+    if (neighbors_were_blocked) { /* :3259-3264 */
+      if (nq < cap_requeue) requeue_nodes[nq] = node; else rc = -1;
+      nq += 1;
+    }
+  }
+  free(cand);
+  free(marks);
+  *n_restored = nr;
+  *n_requeue = nq;
+  return rc;
+}
+
 /* ------------------------------------------------ Dubins trajectory (solver) */
 
 /* DRRT_distance_functions.jl:62-80 */

@@ -211,6 +211,25 @@ int orc_edge_check_dubins(const orc_obstacle2d *ob, const double *start_pos,
                           int32_t n_traj, double robot_radius,
                           double min_turn_radius);
 
+/* addNewObstacle / removeObstacle of the Otte generation with DubinsEdge (DRRT.jl:3048-3268), geometric
+ * decisions only.  Candidates: kdFindWithinRange(KD, ((rho+delta)+ob.radius)+pi, [ob.x ob.y 0.0 pi]) when
+ * has_theta (d = 4 tree with the theta wrap), else (rho+delta)+ob.radius about ob.position.  Graph as in the
+ * sphere sweeps (out-edge CSR; edge id = CSR position; parent[] = end node of rrtParentEdge or -1).  Trajectories
+ * (edge.trajectory[:,1:2]) as one CSR over the ITEMS: item e < n_edges is CSR edge e, item n_edges + v is the
+ * parent edge of node v (traj_ptr has n_edges + n_nodes + 1 entries).  Edge test: orc_edge_check_dubins. */
+int orc_obstacle_add_sweep_2d(const orc_kdtree *t, const orc_obstacle2d *ob, int has_theta, double robot_radius,
+                              double delta, double min_turn_radius, const int64_t *row_ptr, const int32_t *col,
+                              const int32_t *parent, const int64_t *traj_ptr, const double *traj_xy,
+                              int32_t *blocked_edges, int64_t *n_blocked, int64_t cap_blocked, int32_t *orphans,
+                              int64_t *n_orphans, int64_t cap_orphans, int64_t *n_candidates,
+                              int64_t *n_edge_tests);
+int orc_obstacle_remove_sweep_2d(const orc_kdtree *t, const orc_obstacle2d *ob, int has_theta,
+                                 const orc_obstacle2d *others, int64_t n_others, double robot_radius, double delta,
+                                 double min_turn_radius, const int64_t *row_ptr, const int32_t *col,
+                                 const int64_t *traj_ptr, const double *traj_xy, const uint8_t *edge_dist_inf,
+                                 int32_t *restored_edges, int64_t *n_restored, int64_t cap_restored,
+                                 int32_t *requeue_nodes, int64_t *n_requeue, int64_t cap_requeue);
+
 /* Dubins calculateTrajectory, space without time (DRRT_DubinsEdge_functions.jl:329-709): six-word
  * solver + arc discretisation at 0.1 rad.  start4/goal4 = [x y t theta].  type: 0 rsl, 1 rsr, 2 rlr,
  * 3 lsr, 4 lsl, 5 lrl, -1 none.  Returns the number of trajectory points (x,y rows; written up to

@@ -72,6 +72,12 @@ SIGNATURES = {
     "rrtqx_edges_set_parents": (i32, [vp, vp, vp, i64]),
     "rrtqx_obstacle_add_sweep": (i32, [vp, vp, vp, i64, f64, f64, u32, C.POINTER(vp)]),
     "rrtqx_obstacle_remove_sweep": (i32, [vp, vp, i32, vp, i64, vp, f64, f64, u32, C.POINTER(vp)]),
+    "rrtqx_edges_set_trajectories": (i32, [vp, vp, vp]),
+    "rrtqx_edges_solve_trajectories": (i32, [vp, f64, C.POINTER(i64)]),
+    "rrtqx_edges_trajectories_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),
+    "rrtqx_edges_trajectories_fetch": (i32, [vp, vp, vp]),
+    "rrtqx_obstacle_add_sweep_2d": (i32, [vp, vp, vp, i64, f64, f64, f64, u32, C.POINTER(vp)]),
+    "rrtqx_obstacle_remove_sweep_2d": (i32, [vp, vp, i32, vp, i64, vp, f64, f64, f64, u32, C.POINTER(vp)]),
     "rrtqx_sweep_result_destroy": (i32, [vp]),
     "rrtqx_sweep_result_sizes": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "rrtqx_sweep_result_fetch": (i32, [vp, vp, vp]),

@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "objects.cuh"
+#include "polygon.cuh"
 
 using namespace rrtqx;
 
@@ -574,6 +575,7 @@ rrtqx_status rrtqx_edges_destroy(rrtqx_edges *e) {
   return guarded(ctx, [&] {
     bind_device(ctx);
     RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e->solved) rrtqx_dubins_result_destroy(e->solved);
     delete e;
   });
 }
@@ -641,6 +643,81 @@ rrtqx_status rrtqx_obstacle_remove_sweep(rrtqx_edges *edges, const rrtqx_spheres
     RQ_REQUIRE(other_ids != nullptr || n_others == 0, "other_ids is NULL");
     if (!*result) *result = new rrtqx_sweep_result();
     obstacle_remove_sweep(edges, spheres, ob_id, other_ids, n_others, edge_dist_inf, robot_radius, delta, flags, *result);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ------------------------------------------- Otte / Dubins sweeps (2-D polygon world)
+rrtqx_status rrtqx_edges_set_trajectories(rrtqx_edges *e, const int64_t *traj_ptr, const double *traj_xy) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    edges_set_trajectories(e, traj_ptr, traj_xy);
+  });
+}
+
+rrtqx_status rrtqx_edges_solve_trajectories(rrtqx_edges *e, double min_turn_radius, int64_t *n_rows_out) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    edges_solve_trajectories(e, min_turn_radius);
+    if (n_rows_out) *n_rows_out = e->traj_rows;
+  });
+}
+
+rrtqx_status rrtqx_edges_trajectories_device(const rrtqx_edges *e, const int64_t **traj_ptr, const double **traj_xy,
+                                             int64_t *n_items, int64_t *n_rows) {
+  if (!e) return RRTQX_ERR_INVALID;
+  if (e->traj_items < 0) return RRTQX_ERR_STATE;
+  if (traj_ptr) *traj_ptr = e->d_traj_ptr;
+  if (traj_xy) *traj_xy = e->d_traj_xy;
+  if (n_items) *n_items = e->traj_items;
+  if (n_rows) *n_rows = e->traj_rows;
+  return RRTQX_OK;
+}
+
+rrtqx_status rrtqx_edges_trajectories_fetch(rrtqx_edges *e, int64_t *traj_ptr, double *traj_xy) {
+  if (!e) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    if (e->traj_items < 0) throw Error(RRTQX_ERR_STATE, "no trajectories are resident");
+    from_device(ctx, traj_ptr, e->d_traj_ptr, (size_t)e->traj_items + 1);
+    from_device(ctx, traj_xy, e->d_traj_xy, (size_t)e->traj_rows * 2);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_obstacle_add_sweep_2d(rrtqx_edges *edges, const rrtqx_polygons *polygons, const int32_t *ob_ids,
+                                         int64_t n_obs, double robot_radius, double delta, double min_turn_radius,
+                                         uint32_t flags, rrtqx_sweep_result **result) {
+  if (!edges || !polygons) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = edges->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(result != nullptr, "result is NULL");
+    RQ_REQUIRE(ob_ids != nullptr || n_obs == 0, "ob_ids is NULL");
+    if (!*result) *result = new rrtqx_sweep_result();
+    obstacle_add_sweep_2d(edges, polygons, ob_ids, n_obs, robot_radius, delta, min_turn_radius, flags, *result);
+    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+rrtqx_status rrtqx_obstacle_remove_sweep_2d(rrtqx_edges *edges, const rrtqx_polygons *polygons, int32_t ob_id,
+                                            const int32_t *other_ids, int64_t n_others, const uint8_t *edge_dist_inf,
+                                            double robot_radius, double delta, double min_turn_radius, uint32_t flags,
+                                            rrtqx_sweep_result **result) {
+  if (!edges || !polygons) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = edges->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(result != nullptr, "result is NULL");
+    RQ_REQUIRE(other_ids != nullptr || n_others == 0, "other_ids is NULL");
+    if (!*result) *result = new rrtqx_sweep_result();
+    obstacle_remove_sweep_2d(edges, polygons, ob_id, other_ids, n_others, edge_dist_inf, robot_radius, delta,
+                             min_turn_radius, flags, *result);
     RQ_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }

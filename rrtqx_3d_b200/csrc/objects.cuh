@@ -44,6 +44,14 @@ struct rrtqx_edges {
   rrtqx::DevBuf<double> lmax;                 // per node: longest out/parent edge (cull bound)
   rrtqx::DevBuf<uint8_t> degenerate;          // per node: some edge has len == 0 or non-finite ends
   rrtqx::DevBuf<int32_t> scan_tmp;
+  // DubinsEdge trajectories (edge.trajectory[:,1:2]) of the ITEMS = out-edges in upload order, then one parent edge
+  // per node: uploaded (traj_ptr / traj_xy) or solved on the device (`solved`); d_traj_* point at whichever is current
+  rrtqx::DevBuf<int64_t> traj_ptr;
+  rrtqx::DevBuf<double> traj_xy, solve_starts, solve_goals;
+  struct rrtqx_dubins_result *solved = nullptr;
+  const int64_t *d_traj_ptr = nullptr;
+  const double *d_traj_xy = nullptr;
+  int64_t traj_items = -1, traj_rows = 0;  // items the resident trajectories were made for (-1: none)
 };
 
 struct rrtqx_sweep_result {
@@ -63,6 +71,7 @@ struct rrtqx_sweep_result {
   rrtqx::DevBuf<unsigned char> grid;
   rrtqx::DevBuf<int32_t> ids_stage, ids_stage2;
   rrtqx::DevBuf<uint8_t> inf_stage;
+  rrtqx::DevBuf<unsigned char> filt2d;  // start-node filters of the Otte / Dubins sweeps (sweep2d.cu)
 };
 
 namespace rrtqx {
@@ -92,4 +101,15 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
 void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id, const int32_t *other_ids,
                            int64_t n_others, const uint8_t *edge_dist_inf, double robot_radius, double delta,
                            uint32_t flags, rrtqx_sweep_result *R);
+void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R);   // zeroed flag arrays for the current edge set
+void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R);           // flags -> ascending id lists + counts
+// sweep2d.cu
+void edges_set_trajectories(rrtqx_edges *E, const int64_t *traj_ptr, const double *traj_xy);
+void edges_solve_trajectories(rrtqx_edges *E, double min_turn_radius);
+void obstacle_add_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *P, const int32_t *ob_ids, int64_t n_obs,
+                           double robot_radius, double delta, double min_turn_radius, uint32_t flags,
+                           rrtqx_sweep_result *R);
+void obstacle_remove_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *P, int32_t ob_id, const int32_t *other_ids,
+                              int64_t n_others, const uint8_t *edge_dist_inf, double robot_radius, double delta,
+                              double min_turn_radius, uint32_t flags, rrtqx_sweep_result *R);
 }  // namespace rrtqx

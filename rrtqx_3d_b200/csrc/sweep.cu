@@ -129,8 +129,8 @@ void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
   rrtqx_tree *t = E->tree;
   rrtqx_ctx *ctx = t->ctx;
   cudaStream_t st = ctx->stream;
-  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
   RQ_REQUIRE(ne >= 0 && ne < (int64_t)0x7fffffff, "n_edges out of range");
+  E->traj_items = -1;  // resident trajectories belong to the previous edge set
   const int64_t nn = t->n;
   RQ_REQUIRE(parent == nullptr || n_parent == nn, "parent array must have one entry per tree node");
   validate_endpoints(t, src, dst, ne, nn);
@@ -158,7 +158,6 @@ void edges_append(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_
   rrtqx_tree *t = E->tree;
   rrtqx_ctx *ctx = t->ctx;
   cudaStream_t st = ctx->stream;
-  RQ_REQUIRE(t->d == 3, "edge sets / sweeps are implemented for the 3-D SimpleEdge world (d == 3)");
   RQ_REQUIRE(n_new >= 0 && E->n_edges + n_new < (int64_t)0x7fffffff, "n_edges out of range");
   if (n_new == 0) return;
   validate_endpoints(t, src, dst, n_new, t->n);
@@ -512,7 +511,7 @@ compact_tiles_kernel(const uint8_t *__restrict__ flag, int64_t n, const int32_t 
     if (f[k]) out[pos++] = (int32_t)(base + k);
 }
 
-static void finish_sweep(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
+void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   cudaStream_t st = ctx->stream;
   static_assert(SCAN_ITEMS == 8, "compact_tiles_kernel reads 8 flags per thread as one 64-bit word");
   const int64_t et = (R->n_edges + SCAN_TILE - 1) / SCAN_TILE, nt = (R->n_nodes + SCAN_TILE - 1) / SCAN_TILE;
@@ -545,7 +544,7 @@ static void finish_sweep(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   post_launch(ctx, 6);
 }
 
-static void prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
+void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
   rrtqx_ctx *ctx = E->tree->ctx;
   cudaStream_t st = ctx->stream;
   R->ctx = ctx;
@@ -563,13 +562,14 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
                         double robot_radius, double delta, uint32_t flags, rrtqx_sweep_result *R) {
   rrtqx_ctx *ctx = E->tree->ctx;
   cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(E->tree->d == 3, "the sphere-world sweeps need a 3-D tree (SimpleEdge); Dubins trees use the *_2d sweeps");
   RQ_REQUIRE(n_obs >= 0 && n_obs < (1 << 24), "n_obs out of range");
   if (!is_device_ptr(ob_ids))
     for (int64_t i = 0; i < n_obs; ++i) RQ_REQUIRE(ob_ids[i] >= 0 && ob_ids[i] < S->n, "obstacle id out of range");
   const int32_t *dids = to_device(ctx, ob_ids, (size_t)n_obs, R->ids_stage);
   if (E->dirty || E->tree->n != E->n_nodes) edges_rebuild(E);  // appended edges / parents / new nodes
   PhaseScope ph(ctx, "add_sweep");
-  prepare_result(E, R);
+  sweep_prepare_result(E, R);
   bool no_stats = false;
   if (n_obs > 0 && E->n_nodes > 0) {
     R->ob_rec.ensure((size_t)n_obs, st);
@@ -622,7 +622,7 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
     post_launch(ctx, 2);
     }
   }
-  finish_sweep(ctx, R);
+  sweep_finish(ctx, R);
   if (no_stats) { R->n_candidates = -1; R->n_pair_tests = -1; }
 }
 
@@ -631,6 +631,7 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
                            uint32_t flags, rrtqx_sweep_result *R) {
   rrtqx_ctx *ctx = E->tree->ctx;
   cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(E->tree->d == 3, "the sphere-world sweeps need a 3-D tree (SimpleEdge); Dubins trees use the *_2d sweeps");
   RQ_REQUIRE(ob_id >= 0 && ob_id < S->n, "obstacle id out of range");
   RQ_REQUIRE(n_others >= 0 && n_others < (1 << 24), "n_others out of range");
   RQ_REQUIRE(edge_dist_inf != nullptr || E->n_edges == 0, "edge_dist_inf is NULL");
@@ -650,7 +651,7 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
   RQ_CUDA(cudaStreamSynchronize(st));  // ids is a local vector
   const uint8_t *dinf = to_device(ctx, edge_dist_inf, (size_t)E->n_edges, R->inf_stage);
   PhaseScope ph(ctx, "remove_sweep");
-  prepare_result(E, R);
+  sweep_prepare_result(E, R);
   const int n_tab = (int)ids.size();
   R->ob_rec.ensure((size_t)n_tab, st);
   R->ob_par.ensure((size_t)n_tab, st);
@@ -669,7 +670,7 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
                                                                        R->node_flag.p, R->stats.p);
     post_launch(ctx);
   }
-  finish_sweep(ctx, R);
+  sweep_finish(ctx, R);
 }
 
 }  // namespace rrtqx

@@ -317,6 +317,13 @@ class SweepResult:
         A.check(self.L.rrtqx_sweep_result_fetch(self.h, A.ptr(e), A.ptr(n)), self.ctx.h)
         return e, n
 
+    def flags(self, n_edges: int, n_nodes: int):
+        """The same result as byte flags: edge_flag[n_edges], node_flag[n_nodes] (sizes of the swept edge set)."""
+        ef = np.empty(int(n_edges), dtype=np.uint8)
+        nf = np.empty(int(n_nodes), dtype=np.uint8)
+        A.check(self.L.rrtqx_sweep_result_flags(self.h, A.ptr(ef), A.ptr(nf)), self.ctx.h)
+        return ef, nf
+
 
 class EdgeSet:
     """rrtqx_edges: device mirror of the planner's out-edge lists + parents."""
@@ -380,6 +387,52 @@ class EdgeSet:
         A.check(self.L.rrtqx_obstacle_remove_sweep(self.h, spheres.h, int(ob_id), A.ptr(other_ids) if other_ids.size else None,
                                                    other_ids.size, A.ptr(inf), float(robot_radius), float(delta),
                                                    int(flags), C.byref(result.h)), self.ctx.h)
+        return result
+
+
+    # ---- DubinsEdge world (Otte generation, DRRT.jl:3048-3268) -------------------------------------------
+    def set_trajectories(self, traj_ptr, traj_xy):
+        """Upload edge.trajectory[:,1:2] of every ITEM (out-edges in upload order, then one parent edge per node)
+        as a CSR: traj_ptr[n_edges + n_nodes + 1], traj_xy rows x 2."""
+        if isinstance(traj_ptr, (np.ndarray, list, tuple)):
+            traj_ptr = np.ascontiguousarray(traj_ptr, dtype=np.int64)
+            traj_xy = A.as_f64(traj_xy, 2)
+        A.check(self.L.rrtqx_edges_set_trajectories(self.h, A.ptr(traj_ptr), A.ptr(traj_xy) if traj_xy is not None and
+                                                    (not isinstance(traj_xy, np.ndarray) or traj_xy.size) else None), self.ctx.h)
+
+    def solve_trajectories(self, min_turn_radius) -> int:
+        """calculateTrajectory of every item on the device (DRRT_DubinsEdge_functions.jl:329-709); returns the rows."""
+        n = A.i64(0)
+        A.check(self.L.rrtqx_edges_solve_trajectories(self.h, float(min_turn_radius), C.byref(n)), self.ctx.h)
+        return int(n.value)
+
+    def trajectories(self):
+        """Resident trajectories copied to the host: (traj_ptr int64[items + 1], traj_xy float64[rows, 2])."""
+        ni, nr = A.i64(0), A.i64(0)
+        A.check(self.L.rrtqx_edges_trajectories_device(self.h, None, None, C.byref(ni), C.byref(nr)), self.ctx.h)
+        ptr = np.empty(ni.value + 1, dtype=np.int64)
+        xy = np.empty((nr.value, 2), dtype=np.float64)
+        A.check(self.L.rrtqx_edges_trajectories_fetch(self.h, A.ptr(ptr), A.ptr(xy) if xy.size else None), self.ctx.h)
+        return ptr, xy
+
+    def add_sweep_2d(self, polys, ob_ids, robot_radius, delta, min_turn_radius, flags=0, result: SweepResult | None = None):
+        ob_ids = A.as_i32(ob_ids)
+        if result is None:
+            result = SweepResult(self.ctx)
+        A.check(self.L.rrtqx_obstacle_add_sweep_2d(self.h, polys.h, A.ptr(ob_ids), ob_ids.size, float(robot_radius),
+                                                   float(delta), float(min_turn_radius), int(flags), C.byref(result.h)),
+                self.ctx.h)
+        return result
+
+    def remove_sweep_2d(self, polys, ob_id, other_ids, edge_dist_inf, robot_radius, delta, min_turn_radius, flags=0,
+                        result: SweepResult | None = None):
+        other_ids = A.as_i32(other_ids)
+        inf = A.as_u8(np.asarray(edge_dist_inf).astype(np.uint8))
+        if result is None:
+            result = SweepResult(self.ctx)
+        A.check(self.L.rrtqx_obstacle_remove_sweep_2d(self.h, polys.h, int(ob_id), A.ptr(other_ids) if other_ids.size else None,
+                                                      other_ids.size, A.ptr(inf), float(robot_radius), float(delta),
+                                                      float(min_turn_radius), int(flags), C.byref(result.h)), self.ctx.h)
         return result
 
 

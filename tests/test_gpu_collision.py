@@ -446,7 +446,8 @@ def test_cached_obstacle_tables_follow_updates(ctx):
     dst = ((src.astype(np.int64) + 1 + (u[20000:] % np.uint64(40)).astype(np.int64)) % len(pts)).astype(np.int32)
     c, r = W.c3_obstacles(64)
     S = SphereSet(ctx, c, r)
-    S2 = SphereSet(ctx, c[::-1].copy() * 0.5, r[::-1].copy())
+    c2, r2 = c[::-1].copy() * 0.5, r[::-1].copy()
+    S2 = SphereSet(ctx, c2, r2)
     import os
     for forced in (False, True):
         if forced:
@@ -462,7 +463,7 @@ def test_cached_obstacle_tables_follow_updates(ctx):
                 sph_all, _ = oracle.make_spheres(c, r)
                 assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS, flags=A.CHECK_IGNORE_ACTIVE),
                                       _orc_edges(sph_all, ns, pts, src, dst, W.ROBOT_RADIUS))
-                sph2, ns2 = oracle.make_spheres(c[::-1].copy() * 0.5, r[::-1].copy())
+                sph2, ns2 = oracle.make_spheres(c2, r2)
                 assert np.array_equal(edge_check_batch(t, S2, src, dst, W.ROBOT_RADIUS), _orc_edges(sph2, ns2, pts, src, dst, W.ROBOT_RADIUS))
                 act[step * 16:(step + 1) * 16:2] = 0
                 r = r.copy()
