@@ -455,6 +455,7 @@ def test_cached_obstacle_tables_follow_updates(ctx):
         ctx.reload_tuning()
         try:
             act = np.ones(64, np.uint8)
+            S.update(0, radii=r, active=act)
             for step in range(4):
                 sph, ns = oracle.make_spheres(c, r, unused=1 - act)
                 for rho in (W.ROBOT_RADIUS, 1.25):
