@@ -18,7 +18,31 @@ struct NearestScratchHolder {
 };
 static const char g_nearest_tag = 0;  // key of the per-tree nearest-query scratch (rrtqx_tree::scratch)
 
+namespace rrtqx {
+static std::set<const void *> g_live_handles;
+static std::mutex g_live_mutex;
+void handle_register(const void *h) { std::lock_guard<std::mutex> lk(g_live_mutex); g_live_handles.insert(h); }
+void handle_unregister(const void *h) { std::lock_guard<std::mutex> lk(g_live_mutex); g_live_handles.erase(h); }
+bool handle_live(const void *h) { std::lock_guard<std::mutex> lk(g_live_mutex); return g_live_handles.count(h) != 0; }
+}  // namespace rrtqx
+
 namespace {
+// Destroy a child object whose parent context may already be gone (finalizers run in any order): with a live
+// context the stream is drained first; without one the memory is simply released.
+template <typename T>
+rrtqx_status destroy_child(rrtqx_ctx *ctx, T *obj) {
+  if (!obj) return RRTQX_OK;
+  if (ctx && handle_live(ctx)) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  } else {
+    cudaDeviceSynchronize();
+  }
+  delete obj;
+  cudaGetLastError();  // a failed synchronise of a dying context must not poison the next launch check
+  return RRTQX_OK;
+}
+
 template <typename F>
 rrtqx_status guarded(rrtqx_ctx *ctx, F &&f) {
   try {
@@ -71,12 +95,14 @@ rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream, rrtqx_ctx **out
       RQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       c->own_stream = true;
     }
+    handle_register(c);
     *out = c;
   });
 }
 
 rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx) {
-  if (!ctx) return RRTQX_OK;
+  if (!ctx || !handle_live(ctx)) return RRTQX_OK;
+  handle_unregister(ctx);
   return guarded(nullptr, [&] {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -184,18 +210,15 @@ rrtqx_status rrtqx_tree_create(rrtqx_ctx *ctx, int32_t d, int32_t num_wraps, con
       t->wrap.wraps[i] = wraps[i];
       t->wrap.wrap_points[i] = wrap_points[i];
     }
+    handle_register(t);
     *out = t;
   });
 }
 
 rrtqx_status rrtqx_tree_destroy(rrtqx_tree *tree) {
-  if (!tree) return RRTQX_OK;
-  rrtqx_ctx *ctx = tree->ctx;
-  return guarded(ctx, [&] {
-    bind_device(ctx);
-    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    delete tree;  // frees the per-tree scratch (nearest sort buffers, extend_query state) with it
-  });
+  if (!tree || !handle_live(tree)) return RRTQX_OK;
+  handle_unregister(tree);
+  return destroy_child(tree->ctx, tree);  // frees the per-tree scratch (nearest sort buffers, extend_query state) with it
 }
 
 rrtqx_status rrtqx_tree_insert_batch(rrtqx_tree *tree, const double *positions, int64_t n, int32_t *first_index_out) {
@@ -360,14 +383,7 @@ rrtqx_status rrtqx_range_query_batch(rrtqx_tree *tree, const double *queries, in
   });
 }
 
-rrtqx_status rrtqx_range_result_destroy(rrtqx_range_result *r) {
-  if (!r) return RRTQX_OK;
-  rrtqx_ctx *ctx = r->ctx;
-  return guarded(ctx, [&] {
-    if (ctx) { bind_device(ctx); RQ_CUDA(cudaStreamSynchronize(ctx->stream)); }
-    delete r;
-  });
-}
+rrtqx_status rrtqx_range_result_destroy(rrtqx_range_result *r) { return r ? destroy_child(r->ctx, r) : RRTQX_OK; }
 
 rrtqx_status rrtqx_range_result_sizes(const rrtqx_range_result *r, int64_t *n_queries, int64_t *total) {
   if (!r) return RRTQX_ERR_INVALID;
@@ -448,15 +464,7 @@ rrtqx_status rrtqx_spheres_create(rrtqx_ctx *ctx, rrtqx_spheres **out) {
   });
 }
 
-rrtqx_status rrtqx_spheres_destroy(rrtqx_spheres *s) {
-  if (!s) return RRTQX_OK;
-  rrtqx_ctx *ctx = s->ctx;
-  return guarded(ctx, [&] {
-    bind_device(ctx);
-    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    delete s;
-  });
-}
+rrtqx_status rrtqx_spheres_destroy(rrtqx_spheres *s) { return s ? destroy_child(s->ctx, s) : RRTQX_OK; }
 
 __global__ void spheres_pack_kernel(const double *__restrict__ centers, const double *__restrict__ radii, int64_t first,
                                     int64_t n, double4 *__restrict__ rec) {
@@ -571,13 +579,9 @@ rrtqx_status rrtqx_edges_create(rrtqx_tree *tree, rrtqx_edges **out) {
 
 rrtqx_status rrtqx_edges_destroy(rrtqx_edges *e) {
   if (!e) return RRTQX_OK;
-  rrtqx_ctx *ctx = e->tree->ctx;
-  return guarded(ctx, [&] {
-    bind_device(ctx);
-    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (e->solved) rrtqx_dubins_result_destroy(e->solved);
-    delete e;
-  });
+  rrtqx_ctx *ctx = handle_live(e->tree) ? e->tree->ctx : nullptr;  // the tree may have been finalized first
+  if (e->solved) rrtqx_dubins_result_destroy(e->solved);
+  return destroy_child(ctx, e);
 }
 
 rrtqx_status rrtqx_edges_upload(rrtqx_edges *e, const int32_t *src, const int32_t *dst, int64_t n_edges,
@@ -722,14 +726,7 @@ rrtqx_status rrtqx_obstacle_remove_sweep_2d(rrtqx_edges *edges, const rrtqx_poly
   });
 }
 
-rrtqx_status rrtqx_sweep_result_destroy(rrtqx_sweep_result *r) {
-  if (!r) return RRTQX_OK;
-  rrtqx_ctx *ctx = r->ctx;
-  return guarded(ctx, [&] {
-    if (ctx) { bind_device(ctx); RQ_CUDA(cudaStreamSynchronize(ctx->stream)); }
-    delete r;
-  });
-}
+rrtqx_status rrtqx_sweep_result_destroy(rrtqx_sweep_result *r) { return r ? destroy_child(r->ctx, r) : RRTQX_OK; }
 
 rrtqx_status rrtqx_sweep_result_sizes(const rrtqx_sweep_result *r, int64_t *n_edge_hits, int64_t *n_node_hits,
                                       int64_t *n_candidates, int64_t *n_pair_tests) {

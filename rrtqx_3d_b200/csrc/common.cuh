@@ -202,6 +202,13 @@ struct rrtqx_ctx {
 
 namespace rrtqx {
 
+// Registry of live contexts and trees.  Garbage-collected hosts (Julia finalizers, Python __del__) destroy handles
+// in arbitrary order, so a child (tree, obstacle set, edge set, result) may be destroyed AFTER its context / tree:
+// the destroy entry points ask here before they touch the parent, and free the child's memory without it.
+void handle_register(const void *h);
+void handle_unregister(const void *h);
+bool handle_live(const void *h);
+
 // RAII phase timer
 struct PhaseScope {
   rrtqx_ctx *c;

@@ -296,11 +296,15 @@ rrtqx_status rrtqx_dubins_trajectory_batch(rrtqx_ctx *ctx, const double *starts,
 rrtqx_status rrtqx_dubins_result_destroy(rrtqx_dubins_result *r) {
   if (!r) return RRTQX_OK;
   rrtqx_ctx *ctx = r->ctx;
-  return guarded_d(ctx, [&] {
-    RQ_CUDA(cudaSetDevice(ctx->device));
-    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    delete r;
-  });
+  if (ctx && handle_live(ctx)) {  // finalizers run in any order: the context may be gone already
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  } else {
+    cudaDeviceSynchronize();
+  }
+  delete r;
+  cudaGetLastError();
+  return RRTQX_OK;
 }
 
 rrtqx_status rrtqx_dubins_result_sizes(const rrtqx_dubins_result *r, int64_t *n_edges, int64_t *n_rows) {

@@ -113,11 +113,15 @@ rrtqx_status rrtqx_polygons_create(rrtqx_ctx *ctx, rrtqx_polygons **out) {
 rrtqx_status rrtqx_polygons_destroy(rrtqx_polygons *p) {
   if (!p) return RRTQX_OK;
   rrtqx_ctx *ctx = p->ctx;
-  return guarded_p(ctx, [&] {
-    RQ_CUDA(cudaSetDevice(ctx->device));
-    RQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    delete p;
-  });
+  if (ctx && handle_live(ctx)) {  // finalizers run in any order: the context may be gone already
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  } else {
+    cudaDeviceSynchronize();
+  }
+  delete p;
+  cudaGetLastError();
+  return RRTQX_OK;
 }
 
 rrtqx_status rrtqx_polygons_upload(rrtqx_polygons *p, const int32_t *kind, const double *centers,

@@ -506,3 +506,35 @@ def test_contexts_come_and_go():
     for cx, t, S, res in alive:
         assert np.array_equal(edge_check_batch(t, S, src, dst, W.ROBOT_RADIUS), want)
         res.close(); S.close(); t.close(); cx.close()
+
+
+def test_handles_may_be_destroyed_in_any_order():
+    """Garbage-collected hosts (Julia finalizers, Python __del__ of objects in reference cycles) destroy handles in
+    arbitrary order: the context before its trees, a tree before its edge set and results.  Nothing may crash or
+    leave a CUDA error behind for the next call."""
+    from rrtqx_3d_b200.device import Context, EdgeSet
+    pts, qs, r = W.c2_workload(5000, 100)
+    c, rad = W.c3_obstacles(16)
+    src = np.arange(4000, dtype=np.int32)
+    dst = (src + 3) % 5000
+    for order in ("ctx_first", "tree_first"):
+        cx = Context(0)
+        t = DeviceTree(cx, 3)
+        t.insert_batch(pts)
+        S = SphereSet(cx, c, rad)
+        E = EdgeSet(t)
+        E.upload(src, dst, None)
+        res, _ = t.range_query(qs, r)
+        sw = E.add_sweep(S, np.arange(16, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA)
+        if order == "ctx_first":
+            cx.close(); sw.close(); E.close(); res.close(); S.close(); t.close()
+        else:
+            t.close(); E.close(); res.close(); sw.close(); cx.close(); S.close()
+        cx.close(); t.close()          # a second destroy of a dead handle is a no-op
+        # a fresh context right afterwards sees no stale error
+        c2 = Context(0)
+        t2 = DeviceTree(c2, 3)
+        t2.insert_batch(pts)
+        S2 = SphereSet(c2, c, rad)
+        assert edge_check_batch(t2, S2, src, dst, W.ROBOT_RADIUS).shape == (4000,)
+        S2.close(); t2.close(); c2.close()
