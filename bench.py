@@ -124,12 +124,50 @@ def cpu_range_baseline(pts, qs, r, seconds_target=12.0, nthreads=None):
             "mean_neighbours": float(counts.mean())}, tree
 
 
+def julia_reference_rate(pts, qs, r, seconds=20.0):
+    """The REAL reference (Julia) on a sample of the workload, when a `julia` binary and the reference tree
+    (RRTQX_REFERENCE_DIR=<...>/code_RRTQx_3D) are present; None otherwise.  Single-threaded, like the reference."""
+    import shutil
+    import subprocess
+    import tempfile
+    ref = os.environ.get("RRTQX_REFERENCE_DIR")
+    if not shutil.which("julia") or not ref or not os.path.isdir(ref):
+        return None
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as td:
+        fp, fq = os.path.join(td, "p.f64"), os.path.join(td, "q.f64")
+        np.ascontiguousarray(pts, dtype=np.float64).tofile(fp)
+        nq = min(len(qs), 20000)
+        np.ascontiguousarray(qs[:nq], dtype=np.float64).tofile(fq)
+        try:
+            out = subprocess.run(["julia", os.path.join(here, "julia", "bench_reference.jl"), ref, fp, fq, str(len(pts)),
+                                  str(nq), repr(float(r)), str(seconds)], capture_output=True, text=True, timeout=1800).stdout
+            kv = dict(t.split("=") for t in out.strip().split() if "=" in t)
+            return {"value": float(kv["queries_per_s"]), "unit": "queries/s", "cores": 1, "kind": "reference",
+                    "sample": f"{kv['queries']} C2 queries through the reference's kdFindWithinRange (Julia, 1 thread)"}
+        except Exception as exc:  # a broken Julia installation must not take the bench down
+            return {"error": repr(exc)}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (oracle port; Julia is not in the image)."""
+    """--impl reference: the reference's own CPU algorithm -- the Julia reference itself when `julia` and
+    RRTQX_REFERENCE_DIR are present (julia/bench_reference.jl), else the oracle port (no Julia in this image)."""
     if rank != 0:
         return
     nthreads = os.cpu_count() or 1
     pts, qs, r = W.c2_workload(args.nodes, args.queries)
+    jl = julia_reference_rate(pts, qs, r)
+    if jl and "value" in jl:
+        line = {"impl": "reference", "metric": "kd_range_queries_per_s", "value": jl["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2 batched neighbour sweep: 1M-node uniform 3-D tree, kdFindWithinRange at the RRTx "
+                                       "shrinking-ball radius, idx + distance keys", "nodes": args.nodes,
+                           "queries_per_gpu": args.queries, "radius": r, "cpu_arm": jl["sample"]},
+                "cpu_baseline": jl,
+                "e2e": {"value": jl["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     import oracle
     tree = oracle.KDTree(3)
     tree.insert_batch(pts)
@@ -604,8 +642,34 @@ def main():
                        "h2d_bytes_per_step": args.queries * 24,
                        "d2h_bytes_per_step": args.queries * 12 + tot * 12,
                        "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
-                       "note": "pinned host queries -> rrtqx_range_query_batch -> counts/offsets/idx/dist copied to pinned host"}
+                       "note": "pinned host queries -> rrtqx_range_query_batch -> counts/offsets/idx/dist copied to pinned host (rrtqx_host_alloc gives a Julia caller the same kind of memory)"}
         del h_idx, h_dist
+        if world == 1:
+            # the same call with ORDINARY (pageable) host arrays -- what a Julia caller passes when it hands over plain
+            # `Vector`s instead of memory from rrtqx_host_alloc; the driver stages every copy
+            try:
+                pq = np.array(qs, copy=True)
+                p_counts, p_offsets = np.empty(args.queries, np.int32), np.empty(args.queries, np.int64)
+                p_idx, p_dist = np.empty(K + 16, np.int32), np.empty(K + 16, np.float64)
+
+                def pageable_step():
+                    _, tot = tree.range_query(pq, r, want_dist=True, result=res2)
+                    A.check(ctx.L.rrtqx_range_result_layout(res2.h, p_counts.ctypes.data, p_offsets.ctypes.data), ctx.h)
+                    A.check(ctx.L.rrtqx_range_result_fetch(res2.h, p_idx.ctypes.data, p_dist.ctypes.data), ctx.h)
+                    return tot
+
+                pageable_step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    pageable_step()
+                torch.cuda.synchronize()
+                pms = 1e3 * (time.perf_counter() - t0) / 2
+                line["e2e_pageable"] = {"value": args.queries / (pms / 1e3), "unit": "queries/s", "ms_per_step": pms,
+                                        "note": "as e2e, but every host array is ordinary pageable memory (wall clock, 2 steps)"}
+                del p_idx, p_dist
+            except Exception as exc:
+                line["e2e_pageable"] = {"error": repr(exc)}
         res2.close()
 
     # ------------------------------------------------- extra: C3 obstacle-add sweep

@@ -78,6 +78,15 @@ RRTQX_API const char *rrtqx_last_error(const rrtqx_ctx *ctx);
  * environment. */
 RRTQX_API rrtqx_status rrtqx_ctx_reload_tuning(rrtqx_ctx *ctx);
 RRTQX_API rrtqx_status rrtqx_ctx_sync(rrtqx_ctx *ctx);
+/* Page-locked ("pinned") host memory for query / result arrays.  Every entry
+ * point accepts ordinary (pageable) host pointers too -- Julia `Vector`s under
+ * GC.@preserve -- but the driver then stages the copies at a fraction of the
+ * PCIe rate; arrays that are reused across calls should live here (in Julia:
+ * unsafe_wrap(Array, Ptr{T}(p), n) over the returned pointer).  Free with
+ * rrtqx_host_free (ctx may be NULL there). */
+RRTQX_API rrtqx_status rrtqx_host_alloc(rrtqx_ctx *ctx, int64_t bytes,
+                                        void **out);
+RRTQX_API rrtqx_status rrtqx_host_free(rrtqx_ctx *ctx, void *p);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 RRTQX_API rrtqx_status rrtqx_ctx_kernel_launches(const rrtqx_ctx *ctx,
                                                  int64_t *out);

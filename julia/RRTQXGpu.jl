@@ -1,33 +1,50 @@
 # RRTQXGpu.jl -- Julia FFI module for librrtqx_b200.so (include/rrtqx_b200.h).
 #
-# Drop-in for the geometric inner loop of RRTQX_3D: it re-defines, on top of `ccall`s into the
-# hand-written sm_100a library, the generic functions the planner calls
+# Drop-in for the geometric inner loop of RRTQX_3D.  It provides, on top of `ccall`s into the hand-written
+# sm_100a library and WITH THE REFERENCE'S ARGUMENT ORDER, the generic functions the planner calls:
 #
-#   kdInsert, kdFindNearest, kdFindWithinRange, kdFindMoreWithinRange        (kdTree_general.jl:121,357,889,927)
-#   explicitEdgeCheck(S, edge[, ob]), explicitPointCheck, explicitNodeCheck  (DRRT_Q.jl:1802,1520,1594; DRRT_SimpleEdge_functions.jl:210)
-#   findPointsInConflictWithObstacle, addNewObstacle, removeObstacle          (DRRT_Q.jl:3195,3220,3295)
+#   kdInsert(KD, node), kdFindNearest(KD, q), kdFindWithinRange(KD, r, q), kdFindMoreWithinRange(KD, r, q, L)
+#                                                                        (kdTree_general.jl:121,357,889,927)
+#   explicitEdgeCheck(S, edge), explicitEdgeCheck(S, edge, ob)           (DRRT_Q.jl:1802; DRRT_SimpleEdge_functions.jl:210;
+#                                                                         DRRT_DubinsEdge_functions.jl:750)
+#   explicitPointCheck(S, p), explicitPointCheck3D, explicitNodeCheck(S, node), explicitNodeCheck3D
+#                                                                        (DRRT_Q.jl:1520,1558,1594,1595)
+#   findPointsInConflictWithObstacle(S, KD, ob, root)                    (DRRT_Q.jl:3195; DRRT.jl:3048)
+#   addNewObstacle(S, KD, Q, ob, root, fileCounter, R)                   (DRRT_Q.jl:3220; DRRT.jl:3127)
+#   removeObstacle(S, KD, Q, ob, root, hyberBallRad, timeElapsed, moveGoal)   (DRRT_Q.jl:3295; DRRT.jl:3202)
+#   extend(S, KD, Q, newNode, closestNode, delta, hyberBallRad, moveGoal), findBestParent      (julia/extend_gpu.jl)
 #
-# for a tree of type `GpuKDTree{T}`; popFromRangeList / emptyRangeList (kdTree_general.jl:774-787) are
-# unchanged because the results are rebuilt as ordinary JLists with inHeap marks.
+# The device objects that belong to a CSpace (obstacle mirror, resident edge set, the tree) are looked up from `S`
+# in a module-level registry, so no call site of the planner changes its arguments:
 #
-# Usage in an experiment script (after the reference's own includes):
-#     include("RRTQXGpu.jl"); using .RRTQXGpu
+#     include("RRTQXGpu.jl"); using .RRTQXGpu                    # after the reference's own includes
 #     ctx = RRTQXGpu.Context(0)
-#     KD  = RRTQXGpu.GpuKDTree{RRTNode{Float64}}(ctx, S.d, KDdist)          # instead of KDTree{...}(S.d, KDdist)
+#     KD  = RRTQXGpu.GpuKDTree{RRTNode{Float64}}(ctx, S.d, KDdist) # instead of KDTree{RRTNode{Float64}}(S.d, KDdist)
+#     RRTQXGpu.attach!(S, KD)                                      # S -> (ctx, KD, obstacle mirror, edge mirror)
+#     RRTQXGpu.install!()                                          # forwards Main's generic functions (see below)
 #
-# NOTE: there is no Julia in the build image of this repository, so this file is written blind against
-# Julia 1.0 syntax and kept thin; all logic lives behind the C ABI, where it is tested (tests/, via the
-# Python ctypes twin rrtqx_3d_b200/_abi.py which binds the same symbols with the same argument order).
-# There is no CPU fallback: a missing library or GPU is an error().
+# install!() adds methods to the reference's own generic functions in Main.  Those that take the tree dispatch on
+# GpuKDTree (more specific than the reference's untyped methods, nothing is replaced); those that only take the
+# CSpace (explicitEdgeCheck(S, edge), explicitPointCheck(S, p), ...) REPLACE the reference's methods and route an
+# attached S to the GPU.  There is no CPU fallback: an S that was never attached is an error().
+#
+# popFromRangeList / emptyRangeList (kdTree_general.jl:774-787) are unchanged because the results are rebuilt as
+# ordinary JLists with inHeap marks.
+#
+# NOTE: there is no Julia in the build image of this repository, so this file is written blind against Julia 1.0
+# syntax and kept thin; all logic lives behind the C ABI, where it is tested (tests/, via the Python ctypes twin
+# rrtqx_3d_b200/_abi.py which binds the same symbols with the same argument order).  julia/make_reference_vectors.jl
+# is the script to run on the first machine that has Julia 1.x: it pins the CPU oracle against the real reference.
 
 module RRTQXGpu
 
-export Context, GpuKDTree, GpuObstacles, GpuEdges,
+export Context, GpuKDTree, GpuObstacles, GpuPolygons, GpuEdges, GpuWorld, attach!, detach!, install!,
        kdInsert, kdInsertBatch, kdFindNearest, kdFindWithinRange, kdFindMoreWithinRange,
        kdFindWithinRangeBatch, kdFindNearestBatch,
        explicitEdgeCheck, explicitEdgeCheckBatch, explicitPointCheck, explicitPointCheck3D,
        explicitNodeCheck, explicitNodeCheck3D,
-       findPointsInConflictWithObstacle, addNewObstacle, removeObstacle, syncObstacles!, syncEdges!
+       findPointsInConflictWithObstacle, addNewObstacle, removeObstacle, syncObstacles!, syncPolygons!, syncEdges!,
+       extendQuery, pinnedVector
 
 const LIB = get(ENV, "RRTQX_B200_LIB", joinpath(@__DIR__, "..", "rrtqx_3d_b200", "librrtqx_b200.so"))
 
@@ -55,6 +72,16 @@ end
 function check(ctx::Context, st::Int32)
   st == 0 && return nothing
   error("rrtqx status $(st): " * unsafe_string(ccall((:rrtqx_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h)))
+end
+
+# Page-locked host memory (rrtqx_host_alloc): a Vector over pinned memory for arrays that are reused across calls.
+# Ordinary Vectors work everywhere too, but the driver stages their copies at a fraction of the PCIe rate.
+function pinnedVector(ctx::Context, ::Type{T}, n::Integer) where {T}
+  p = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ctx, ccall((:rrtqx_host_alloc, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, Int64(n) * sizeof(T), p))
+  v = unsafe_wrap(Array, Ptr{T}(p[]), Int(n))
+  finalizer(x -> ccall((:rrtqx_host_free, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), C_NULL, pointer(x)), v)
+  return v
 end
 
 # --------------------------------------------------------------------- tree
@@ -212,71 +239,98 @@ mutable struct GpuObstacles
   ctx::Context
   h::Ptr{Cvoid}
   ids::IdDict{Any,Int32}          # obstacle -> device index
+  radii::Vector{Float64}          # what the device holds (change detection)
+  active::Vector{UInt8}
   function GpuObstacles(ctx::Context)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx, ccall((:rrtqx_spheres_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, h))
-    o = new(ctx, h[], IdDict{Any,Int32}())
+    o = new(ctx, h[], IdDict{Any,Int32}(), Float64[], UInt8[])
     finalizer(x -> ccall((:rrtqx_spheres_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), o)
     return o
   end
 end
 
-# active[i] = !(obstacleUnused || lifeSpan <= 0): the early-out of explicitEdgeCheck3D (DRRT_Q.jl:1777)
+# active[i] = !(obstacleUnused || lifeSpan <= 0): the early-out of explicitEdgeCheck3D (DRRT_Q.jl:1777).
+# The obstacle list only grows and only radii / flags change in place (rrtqx.jl:462-530, obstacleAugmentation.jl),
+# so an unchanged list costs one walk and no upload; a grown list is re-uploaded, changed radii / flags are patched.
 function syncObstacles!(G::GpuObstacles, S)
   n = S.obstacles.length
-  centers = Matrix{Float64}(undef, 3, n); radii = Vector{Float64}(undef, n); active = Vector{UInt8}(undef, n)
-  empty!(G.ids)
+  radii = Vector{Float64}(undef, n); active = Vector{UInt8}(undef, n)
+  obs = Vector{Any}(undef, n)
   item = S.obstacles.front
   for i = 1:n
     ob = item.data
-    centers[:, i] = ob.position[1:3]
+    obs[i] = ob
     radii[i] = ob.radius
     active[i] = (ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01
-    G.ids[ob] = Int32(i - 1)
     item = item.child
   end
-  GC.@preserve centers radii active check(G.ctx, ccall((:rrtqx_spheres_upload, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Int64), G.h, centers, radii, active, n))
+  same = n == length(G.radii)
+  if same
+    for i = 1:n
+      if !haskey(G.ids, obs[i]) || G.ids[obs[i]] != Int32(i - 1)
+        same = false
+        break
+      end
+    end
+  end
+  if !same                                     # new / reordered list: full upload
+    centers = Matrix{Float64}(undef, 3, n)
+    empty!(G.ids)
+    for i = 1:n
+      centers[:, i] = obs[i].position[1:3]
+      G.ids[obs[i]] = Int32(i - 1)
+    end
+    GC.@preserve centers radii active check(G.ctx, ccall((:rrtqx_spheres_upload, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Int64), G.h, centers, radii, active, n))
+  elseif radii != G.radii || active != G.active  # in-place update of radius / flags
+    GC.@preserve radii active check(G.ctx, ccall((:rrtqx_spheres_update, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{UInt8}), G.h, 0, n, radii, active))
+  end
+  G.radii = radii; G.active = active
   return G
 end
 
-# explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826), SimpleEdge
-function explicitEdgeCheck(G::GpuObstacles, S, edge, flags::UInt32 = UInt32(0))
-  S.inWarmupTime && return false
-  s = vec(Array{Float64}(edge.startNode.position))[1:3]; e = vec(Array{Float64}(edge.endNode.position))[1:3]
-  out = Vector{UInt8}(undef, 1)
-  GC.@preserve s e out check(G.ctx, ccall((:rrtqx_segment_check_batch, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, UInt32, Ptr{UInt8}),
-      G.ctx.h, G.h, s, e, 1, S.robotRadius, flags, out))
-  return out[1] != 0x00
+# ------------------------------------------------------------------ polygons (Otte generation, DubinsEdge)
+mutable struct GpuPolygons
+  ctx::Context
+  h::Ptr{Cvoid}
+  ids::IdDict{Any,Int32}
+  function GpuPolygons(ctx::Context)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:rrtqx_polygons_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, h))
+    o = new(ctx, h[], IdDict{Any,Int32}())
+    finalizer(x -> ccall((:rrtqx_polygons_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), o)
+    return o
+  end
 end
 
-# batched explicitEdgeCheck over edges between tree nodes given as 1-based index vectors
-function explicitEdgeCheckBatch(G::GpuObstacles, S, tree::GpuKDTree, src::Vector{Int32}, dst::Vector{Int32},
-                                flags::UInt32 = UInt32(0))
-  out = Vector{UInt8}(undef, length(src))
-  S.inWarmupTime && return fill!(out, 0x00)
-  s0 = src .- Int32(1); d0 = dst .- Int32(1)
-  GC.@preserve s0 d0 out check(G.ctx, ccall((:rrtqx_edge_check_batch, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Float64, UInt32, Ptr{UInt8}),
-      tree.h, G.h, s0, d0, length(src), S.robotRadius, flags, out))
-  return out
+# Mirrors S.obstacles (Obstacle kinds 1 and 3, DRRT_data_structures.jl:135-265): bounding circles as the
+# constructor computed them (ob.position, ob.radius), polygon vertices as a CSR.
+function syncPolygons!(G::GpuPolygons, S)
+  kinds = Int32[]; centers = Float64[]; radii = Float64[]; active = UInt8[]; vptr = Int64[0]; verts = Float64[]
+  empty!(G.ids)
+  item = S.obstacles.front
+  for i = 1:S.obstacles.length
+    ob = item.data
+    G.ids[ob] = Int32(i - 1)
+    push!(kinds, Int32(ob.kind)); push!(centers, ob.position[1], ob.position[2]); push!(radii, ob.radius)
+    push!(active, (ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01)
+    if ob.kind == 3
+      for r = 1:size(ob.polygon, 1)
+        push!(verts, ob.polygon[r, 1], ob.polygon[r, 2])
+      end
+    end
+    push!(vptr, length(verts) ÷ 2)
+    item = item.child
+  end
+  GC.@preserve kinds centers radii active vptr verts check(G.ctx, ccall((:rrtqx_polygons_upload, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ptr{Float64}, Int64),
+      G.h, kinds, centers, radii, active, vptr, verts, length(kinds)))
+  return G
 end
 
-function pointCheck(G::GpuObstacles, S, point::Array{Float64}, flags::UInt32)
-  S.inWarmupTime && return (false, Inf)
-  p = vec(Array{Float64}(point))[1:3]; out = Vector{UInt8}(undef, 1); cert = Vector{Float64}(undef, 1)
-  GC.@preserve p out cert check(G.ctx, ccall((:rrtqx_node_check_batch, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, UInt32, Ptr{UInt8}, Ptr{Float64}),
-      G.ctx.h, G.h, p, 1, S.robotRadius, flags, out, cert))
-  return (out[1] != 0x00, cert[1])
-end
-explicitPointCheck(G::GpuObstacles, S, point::Array{Float64}) = pointCheck(G, S, point, CHECK_QUICK_PASS)   # DRRT_Q.jl:1520
-explicitPointCheck3D(G::GpuObstacles, S, point::Array{Float64}) = pointCheck(G, S, point, UInt32(0))        # DRRT_Q.jl:1558
-explicitNodeCheck(G::GpuObstacles, S, node) = explicitPointCheck(G, S, node.position)                       # DRRT_Q.jl:1594
-explicitNodeCheck3D(G::GpuObstacles, S, node) = explicitPointCheck3D(G, S, node.position)                   # DRRT_Q.jl:1595
-
-# -------------------------------------------------------------- edges + sweeps
+# -------------------------------------------------------------- resident edge set
 mutable struct GpuEdges
   tree::GpuKDTree
   h::Ptr{Cvoid}
@@ -295,11 +349,14 @@ mutable struct GpuEdges
 end
 
 # mirrors every node's out-edges in the order of RRTNodeNeighborIterator (DRRT_Q.jl:2408-2431):
-# InitialNeighborListOut, then rrtNeighborsOut; plus the parent edges
-function syncEdges!(E::GpuEdges)
+# InitialNeighborListOut, then rrtNeighborsOut; plus the parent edges.  With withTrajectories (DubinsEdge) the
+# planner's own edge.trajectory rows are uploaded too (items = out-edges, then one parent edge per node), so the
+# Dubins sweeps decide on exactly the points the reference would test.
+function syncEdges!(E::GpuEdges; withTrajectories::Bool = false)
   tree = E.tree
   src = Int32[]; dst = Int32[]; empty!(E.items)
-  parent = fill(Int32(-1), length(tree.nodes))
+  nn = length(tree.nodes)
+  parent = fill(Int32(-1), nn)
   for n in tree.nodes
     for lst in (n.InitialNeighborListOut, n.rrtNeighborsOut)
       item = lst.front
@@ -314,6 +371,27 @@ function syncEdges!(E::GpuEdges)
   end
   GC.@preserve src dst parent check(tree.ctx, ccall((:rrtqx_edges_upload, LIB), Int32,
       (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{Int32}, Int64), E.h, src, dst, length(src), parent, length(parent)))
+  if withTrajectories
+    ne = length(src)
+    ptr = Vector{Int64}(undef, ne + nn + 1); ptr[1] = 0
+    for (i, it) in enumerate(E.items)
+      ptr[i + 1] = ptr[i] + size(it.data.trajectory, 1)
+    end
+    for (v, n) in enumerate(tree.nodes)
+      ptr[ne + v + 1] = ptr[ne + v] + (n.rrtParentUsed ? size(n.rrtParentEdge.trajectory, 1) : 0)
+    end
+    xy = Matrix{Float64}(undef, 2, ptr[ne + nn + 1])
+    for (i, it) in enumerate(E.items)
+      xy[:, ptr[i]+1:ptr[i+1]] = permutedims(it.data.trajectory[:, 1:2])
+    end
+    for (v, n) in enumerate(tree.nodes)
+      if n.rrtParentUsed
+        xy[:, ptr[ne+v]+1:ptr[ne+v+1]] = permutedims(n.rrtParentEdge.trajectory[:, 1:2])
+      end
+    end
+    GC.@preserve ptr xy check(tree.ctx, ccall((:rrtqx_edges_set_trajectories, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}), E.h, ptr, xy))
+  end
   return E
 end
 
@@ -325,83 +403,6 @@ function fetchSweep(E::GpuEdges)
   GC.@preserve edges nodes check(E.tree.ctx, ccall((:rrtqx_sweep_result_fetch, LIB), Int32,
                                                    (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), E.res[], edges, nodes))
   return (edges, nodes)
-end
-
-# findPointsInConflictWithObstacle (DRRT_Q.jl:3195-3215), Euclidean space without time/theta
-function findPointsInConflictWithObstacle(S, KD::GpuKDTree, ob, root)
-  (!S.spaceHasTime && !S.spaceHasTheta) || error("this type of obstacle not coded for this type of space")
-  searchRange = S.robotRadius + S.delta + ob.radius
-  return kdFindWithinRange(KD, searchRange, ob.position)
-end
-
-# addNewObstacle (DRRT_Q.jl:3220-3290): the GPU returns the blocked edge ids and the orphaned node ids,
-# the reference's list surgery is applied here unchanged.
-function addNewObstacle(G::GpuObstacles, E::GpuEdges, S, KD::GpuKDTree, Q, ob, root, fileCounter::Int, R)
-  ob.obstacleUnused = false
-  syncObstacles!(G, S)
-  if ob.lifeSpan > 0
-    ids = Int32[G.ids[ob]]
-    GC.@preserve ids check(KD.ctx, ccall((:rrtqx_obstacle_add_sweep, LIB), Int32,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Int64, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
-        E.h, G.h, ids, 1, S.robotRadius, S.delta, UInt32(0), E.res))
-    (blocked, orphans) = fetchSweep(E)
-    for e in blocked
-      E.items[e + 1].data.dist = Inf                                   # :3248-3249
-    end
-    for v in orphans                                                   # :3257-3270
-      thisNode = KD.nodes[v + 1]
-      Main.JlistRemove(thisNode.rrtParentEdge.endNode.SuccessorList, thisNode.successorListItemInParent)
-      thisNode.rrtParentEdge.endNode = thisNode
-      thisNode.rrtParentEdge.dist = Inf
-      thisNode.rrtParentUsed = false
-      Main.verifyInOSQueue(Q, thisNode)
-    end
-  end
-  if R.robotEdgeUsed                                                   # :3287-3289
-    one = GpuObstacles(G.ctx)
-    c = Array{Float64}(ob.position[1:3]); r = Float64[ob.radius]; a = UInt8[(ob.lifeSpan > 0) ? 0x01 : 0x00]
-    GC.@preserve c r a check(G.ctx, ccall((:rrtqx_spheres_upload, LIB), Int32,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Int64), one.h, c, r, a, 1))
-    if explicitEdgeCheck(one, S, R.robotEdge)
-      R.currentMoveInvalid = true
-    end
-  end
-end
-
-# removeObstacle (DRRT_Q.jl:3295-3362).  qxSemantics = true reproduces this fork (the obstacle is disabled
-# before the loop, so nothing is ever restored); false gives the Otte generation (DRRT.jl:3202-3268).
-function removeObstacle(G::GpuObstacles, E::GpuEdges, S, KD::GpuKDTree, Q, ob, root, hyberBallRad::Float64,
-                        timeElapsed::Float64, moveGoal; qxSemantics::Bool = true)
-  syncObstacles!(G, S)
-  obId = G.ids[ob]
-  ob.expired = true
-  ob.obstacleUnused = true
-  others = Int32[]
-  item = S.obstacles.front
-  for i = 1:S.obstacles.length
-    o = item.data
-    if o != ob && !o.obstacleUnused && o.lifeSpan > 0 && o.startTime <= timeElapsed <= (o.startTime + o.lifeSpan)
-      push!(others, G.ids[o])
-    end
-    item = item.child
-  end
-  inf = UInt8[(it.data.dist == Inf) ? 0x01 : 0x00 for it in E.items]
-  flags = qxSemantics ? SWEEP_REMOVED_INACTIVE : UInt32(0)
-  GC.@preserve others inf check(KD.ctx, ccall((:rrtqx_obstacle_remove_sweep, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Int64, Ptr{UInt8}, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
-      E.h, G.h, obId, others, length(others), inf, S.robotRadius, S.delta, flags, E.res))
-  (restored, requeue) = fetchSweep(E)
-  for e in restored
-    E.items[e + 1].data.dist = E.items[e + 1].data.distOriginal        # :3340-3346
-  end
-  for v in requeue                                                     # :3352-3357
-    thisNode = KD.nodes[v + 1]
-    Main.recalculateLMCMineVTwo(Q, thisNode, root, hyberBallRad)
-    if thisNode.rrtTreeCost != thisNode.rrtLMC && Main.lessQ(thisNode, moveGoal)
-      Main.verifyInQueue(Q, thisNode)
-    end
-  end
-  ob.obstacleUnused = true
 end
 
 # ------------------------------------------------------------------ neighbour-graph residency
@@ -420,61 +421,258 @@ function setParents!(E::GpuEdges, nodeIdx::Vector{Int32}, parentIdx::Vector{Int3
       (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64), E.h, nodeIdx, parentIdx, length(nodeIdx)))
 end
 
-# ------------------------------------------------------------------ fused per-iteration query
-# One launch for what extend() asks of the geometry per sample (rrtqx.jl:926-950, DRRT_Q.jl:2551-2637):
-# nearest node, explicitNodeCheck of the sample, the shrinking-ball neighbours with their keys, and
-# explicitEdgeCheck of every new edge in both directions.
-function extendQuery(G::GpuObstacles, S, tree::GpuKDTree, point::Array{Float64}, range::Float64; capacity::Int = 8192)
-  nearestIdx = Ref{Int32}(0); nearestDist = Ref{Float64}(0.0)
-  collides = Ref{UInt8}(0); cert = Ref{Float64}(0.0); n = Ref{Int32}(0)
-  idx = Vector{Int32}(undef, capacity); dist = Vector{Float64}(undef, capacity)
-  fwd = Vector{UInt8}(undef, capacity); rev = Vector{UInt8}(undef, capacity)
-  p = vec(point)
-  GC.@preserve p idx dist fwd rev check(tree.ctx, ccall((:rrtqx_extend_query, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, UInt32, Int32, Ref{Int32}, Ref{Float64}, Ref{UInt8},
-       Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}, Ptr{UInt8}),
-      tree.h, G.h, p, range, S.robotRadius, UInt32(4), Int32(capacity), nearestIdx, nearestDist, collides, cert, n,
-      idx, dist, fwd, rev))
-  k = Int(n[])
-  return (tree.nodes[nearestIdx[] + 1], nearestDist[], collides[] != 0, cert[],
-          idx[1:k], dist[1:k], fwd[1:k] .!= 0, rev[1:k] .!= 0)
-end
-
-# ------------------------------------------------------------------ Dubins edges (2-D polygon world)
-mutable struct GpuPolygons
+# ------------------------------------------------------------------ CSpace -> device objects
+# Everything the reference-order entry points need is found from `S`: the planner's call sites keep their
+# arguments (explicitEdgeCheck(S, edge), addNewObstacle(S, KD, Q, ob, root, fileCounter, R), ...).
+mutable struct GpuWorld
   ctx::Context
-  h::Ptr{Cvoid}
-  function GpuPolygons(ctx::Context)
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ctx, ccall((:rrtqx_polygons_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, h))
-    o = new(ctx, h[])
-    finalizer(x -> ccall((:rrtqx_polygons_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), o)
-    return o
-  end
+  KD::GpuKDTree
+  spheres::GpuObstacles           # mirror of S.obstacles when they are SphereObstacles (QX-3D generation)
+  polygons::GpuPolygons           # mirror of S.obstacles when they are Obstacles (Otte generation, DubinsEdge)
+  edges::GpuEdges                 # resident out-edge lists + parents
+  edgesStale::Bool                # the graph changed since the last syncEdges!
+  single::GpuObstacles            # one-obstacle set for explicitEdgeCheck(S, edge, ob)
+  pinned::Dict{Symbol,Any}        # pinned scratch arrays reused across calls (extendQuery)
 end
 
-# Mirrors S.obstacles (Obstacle kinds 1 and 3, DRRT_data_structures.jl:135-265): bounding circles as the
-# constructor computed them (ob.position, ob.radius), polygon vertices as a CSR.
-function syncPolygons!(G::GpuPolygons, S)
-  kinds = Int32[]; centers = Float64[]; radii = Float64[]; active = UInt8[]; vptr = Int64[0]; verts = Float64[]
-  item = S.obstacles.front
-  for i = 1:S.obstacles.length
-    ob = item.data
-    push!(kinds, Int32(ob.kind)); push!(centers, ob.position[1], ob.position[2]); push!(radii, ob.radius)
-    push!(active, (ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01)
+const WORLDS = IdDict{Any,GpuWorld}()
+
+function attach!(S, KD::GpuKDTree)
+  W = GpuWorld(KD.ctx, KD, GpuObstacles(KD.ctx), GpuPolygons(KD.ctx), GpuEdges(KD), true, GpuObstacles(KD.ctx),
+               Dict{Symbol,Any}())
+  WORLDS[S] = W
+  return W
+end
+detach!(S) = delete!(WORLDS, S)
+function world(S)
+  haskey(WORLDS, S) || error("this CSpace is not attached to a GPU context: RRTQXGpu.attach!(S, KD) first (there is no CPU fallback)")
+  return WORLDS[S]
+end
+# the planner tells the mirror that neighbour lists / parents changed (extend_gpu.jl does it for its own edits);
+# the next sweep re-syncs
+markEdgesStale!(S) = (world(S).edgesStale = true; nothing)
+
+isPolygonWorld(S) = S.obstacles.length > 0 && (:polygon in fieldnames(typeof(S.obstacles.front.data)))
+isDubinsEdge(edge) = :trajectory in fieldnames(typeof(edge))
+
+# ------------------------------------------------------------------ collision checks, reference order
+# explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826 / DRRT.jl:1660-1678): OR over the obstacle list
+function explicitEdgeCheck(S, edge)
+  S.inWarmupTime && return false
+  W = world(S)
+  if isDubinsEdge(edge)
+    syncPolygons!(W.polygons, S)
+    return explicitEdgeCheckBatch(W.polygons, S, Any[edge])[1]
+  end
+  syncObstacles!(W.spheres, S)
+  return segmentCheck(W.spheres, S, edge)
+end
+
+# explicitEdgeCheck(S, edge, ob): ONE obstacle (DRRT_SimpleEdge_functions.jl:210 -> explicitEdgeCheck3D
+# DRRT_Q.jl:1775; DRRT_DubinsEdge_functions.jl:750).  No warm-up short-circuit here, as in the reference.
+function explicitEdgeCheck(S, edge, ob)
+  W = world(S)
+  if isDubinsEdge(edge)
+    one = GpuPolygons(W.ctx)
+    kinds = Int32[ob.kind]; centers = Float64[ob.position[1], ob.position[2]]; radii = Float64[ob.radius]
+    active = UInt8[(ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01]
+    verts = Float64[]
     if ob.kind == 3
       for r = 1:size(ob.polygon, 1)
         push!(verts, ob.polygon[r, 1], ob.polygon[r, 2])
       end
     end
-    push!(vptr, length(verts) ÷ 2)
-    item = item.child
+    vptr = Int64[0, length(verts) ÷ 2]
+    GC.@preserve kinds centers radii active vptr verts check(W.ctx, ccall((:rrtqx_polygons_upload, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ptr{Float64}, Int64),
+        one.h, kinds, centers, radii, active, vptr, verts, 1))
+    return dubinsCheck(one, S, Any[edge])[1]
   end
-  GC.@preserve kinds centers radii active vptr verts check(G.ctx, ccall((:rrtqx_polygons_upload, LIB), Int32,
-      (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ptr{Float64}, Int64),
-      G.h, kinds, centers, radii, active, vptr, verts, length(kinds)))
+  c = Array{Float64}(vec(ob.position)[1:3]); r = Float64[ob.radius]
+  a = UInt8[(ob.obstacleUnused || ob.lifeSpan <= 0) ? 0x00 : 0x01]
+  GC.@preserve c r a check(W.ctx, ccall((:rrtqx_spheres_upload, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Int64), W.single.h, c, r, a, 1))
+  return segmentCheck(W.single, S, edge)
 end
 
+function segmentCheck(G::GpuObstacles, S, edge, flags::UInt32 = UInt32(0))
+  s = vec(Array{Float64}(edge.startNode.position))[1:3]; e = vec(Array{Float64}(edge.endNode.position))[1:3]
+  out = Vector{UInt8}(undef, 1)
+  GC.@preserve s e out check(G.ctx, ccall((:rrtqx_segment_check_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, UInt32, Ptr{UInt8}),
+      G.ctx.h, G.h, s, e, 1, S.robotRadius, flags, out))
+  return out[1] != 0x00
+end
+
+# batched explicitEdgeCheck over edges between tree nodes given as 1-based index vectors (SimpleEdge)
+function explicitEdgeCheckBatch(S, tree::GpuKDTree, src::Vector{Int32}, dst::Vector{Int32}, flags::UInt32 = UInt32(0))
+  out = Vector{UInt8}(undef, length(src))
+  S.inWarmupTime && return fill!(out, 0x00)
+  G = syncObstacles!(world(S).spheres, S)
+  s0 = src .- Int32(1); d0 = dst .- Int32(1)
+  GC.@preserve s0 d0 out check(G.ctx, ccall((:rrtqx_edge_check_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Int64, Float64, UInt32, Ptr{UInt8}),
+      tree.h, G.h, s0, d0, length(src), S.robotRadius, flags, out))
+  return out
+end
+
+function pointCheck(S, point::Array{Float64}, flags::UInt32)
+  S.inWarmupTime && return (false, Inf)
+  G = syncObstacles!(world(S).spheres, S)
+  p = vec(Array{Float64}(point))[1:3]; out = Vector{UInt8}(undef, 1); cert = Vector{Float64}(undef, 1)
+  GC.@preserve p out cert check(G.ctx, ccall((:rrtqx_node_check_batch, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, UInt32, Ptr{UInt8}, Ptr{Float64}),
+      G.ctx.h, G.h, p, 1, S.robotRadius, flags, out, cert))
+  return (out[1] != 0x00, cert[1])
+end
+explicitPointCheck(S, point::Array{Float64}) = pointCheck(S, point, CHECK_QUICK_PASS)   # DRRT_Q.jl:1520
+explicitPointCheck3D(S, point::Array{Float64}) = pointCheck(S, point, UInt32(0))        # DRRT_Q.jl:1558
+explicitNodeCheck(S, node) = explicitPointCheck(S, node.position)                       # DRRT_Q.jl:1594
+explicitNodeCheck3D(S, node) = explicitPointCheck3D(S, node.position)                   # DRRT_Q.jl:1595
+
+# ------------------------------------------------------------------ obstacle sweeps, reference order
+# findPointsInConflictWithObstacle (DRRT_Q.jl:3195-3215; Otte DRRT.jl:3048-3064), spaces without time
+function findPointsInConflictWithObstacle(S, KD::GpuKDTree, ob, root)
+  S.spaceHasTime && error("this type of obstacle not coded for this type of space")
+  if !S.spaceHasTheta
+    searchRange = S.robotRadius + S.delta + ob.radius
+    return kdFindWithinRange(KD, searchRange, Array{Float64}(ob.position))
+  end
+  searchRange = S.robotRadius + S.delta + ob.radius + pi          # Dubins robot without time, [x y 0.0 theta]
+  obsCenterDubins = Float64[ob.position[1] ob.position[2] 0.0 pi]
+  return kdFindWithinRange(KD, searchRange, obsCenterDubins)
+end
+
+function ensureEdges!(W::GpuWorld, withTrajectories::Bool)
+  if W.edgesStale
+    syncEdges!(W.edges; withTrajectories = withTrajectories)
+    W.edgesStale = false
+  end
+  return W.edges
+end
+
+# addNewObstacle (DRRT_Q.jl:3220-3290; Otte DRRT.jl:3127-3197): the GPU returns the blocked edge ids and the
+# orphaned node ids, the reference's list surgery is applied here unchanged.
+function addNewObstacle(S, KD::GpuKDTree, Q, ob, root, fileCounter::Int, R)
+  W = world(S)
+  ob.obstacleUnused = false
+  poly = isPolygonWorld(S)
+  E = ensureEdges!(W, poly)
+  if ob.lifeSpan > 0
+    if poly
+      syncPolygons!(W.polygons, S)
+      ids = Int32[W.polygons.ids[ob]]
+      GC.@preserve ids check(KD.ctx, ccall((:rrtqx_obstacle_add_sweep_2d, LIB), Int32,
+          (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Int64, Float64, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
+          E.h, W.polygons.h, ids, 1, S.robotRadius, S.delta, S.minTurningRadius, UInt32(0), E.res))
+    else
+      syncObstacles!(W.spheres, S)
+      ids = Int32[W.spheres.ids[ob]]
+      GC.@preserve ids check(KD.ctx, ccall((:rrtqx_obstacle_add_sweep, LIB), Int32,
+          (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Int64, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
+          E.h, W.spheres.h, ids, 1, S.robotRadius, S.delta, UInt32(0), E.res))
+    end
+    (blocked, orphans) = fetchSweep(E)
+    for e in blocked
+      E.items[e + 1].data.dist = Inf                                   # :3248-3249
+    end
+    for v in orphans                                                   # :3257-3270
+      thisNode = KD.nodes[v + 1]
+      Main.JlistRemove(thisNode.rrtParentEdge.endNode.SuccessorList, thisNode.successorListItemInParent)
+      thisNode.rrtParentEdge.endNode = thisNode
+      thisNode.rrtParentEdge.dist = Inf
+      thisNode.rrtParentUsed = false
+      Main.verifyInOSQueue(Q, thisNode)
+    end
+    if length(orphans) > 0
+      idx = Int32[v for v in orphans]
+      setParents!(E, idx, fill(Int32(-1), length(idx)))                # keep the resident parents in step
+    end
+  end
+  if R.robotEdgeUsed && explicitEdgeCheck(S, R.robotEdge, ob)          # :3287-3289 (per-obstacle form: no warm-up test)
+    R.currentMoveInvalid = true
+  end
+end
+
+# removeObstacle.  SphereObstacle worlds follow this fork (DRRT_Q.jl:3295-3362: the obstacle is disabled BEFORE the
+# loop, so nothing is ever restored -- reproduced by RRTQX_SWEEP_REMOVED_INACTIVE); Obstacle worlds follow the
+# Otte generation (DRRT.jl:3202-3268: still active while tested).  qxSemantics overrides the choice.
+function removeObstacle(S, KD::GpuKDTree, Q, ob, root, hyberBallRad::Float64, timeElapsed::Float64, moveGoal;
+                        qxSemantics::Union{Nothing,Bool} = nothing)
+  W = world(S)
+  poly = isPolygonWorld(S)
+  qx = qxSemantics === nothing ? !poly : qxSemantics
+  E = ensureEdges!(W, poly)
+  ids = poly ? syncPolygons!(W.polygons, S).ids : syncObstacles!(W.spheres, S).ids
+  obId = ids[ob]
+  if qx
+    ob.expired = true
+    ob.obstacleUnused = true                                           # DRRT_Q.jl:3301-3302
+  end
+  others = Int32[]
+  item = S.obstacles.front
+  for i = 1:S.obstacles.length
+    o = item.data
+    if o != ob && !o.obstacleUnused && o.lifeSpan > 0 && o.startTime <= timeElapsed <= (o.startTime + o.lifeSpan)
+      push!(others, ids[o])
+    end
+    item = item.child
+  end
+  inf = UInt8[(it.data.dist == Inf) ? 0x01 : 0x00 for it in E.items]
+  if poly
+    GC.@preserve others inf check(KD.ctx, ccall((:rrtqx_obstacle_remove_sweep_2d, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Int64, Ptr{UInt8}, Float64, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
+        E.h, W.polygons.h, obId, others, length(others), inf, S.robotRadius, S.delta, S.minTurningRadius, UInt32(0), E.res))
+  else
+    flags = qx ? SWEEP_REMOVED_INACTIVE : UInt32(0)
+    GC.@preserve others inf check(KD.ctx, ccall((:rrtqx_obstacle_remove_sweep, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Int64, Ptr{UInt8}, Float64, Float64, UInt32, Ref{Ptr{Cvoid}}),
+        E.h, W.spheres.h, obId, others, length(others), inf, S.robotRadius, S.delta, flags, E.res))
+  end
+  (restored, requeue) = fetchSweep(E)
+  for e in restored
+    E.items[e + 1].data.dist = E.items[e + 1].data.distOriginal        # :3340-3346
+  end
+  for v in requeue                                                     # :3352-3357
+    thisNode = KD.nodes[v + 1]
+    Main.recalculateLMCMineVTwo(Q, thisNode, root, hyberBallRad)
+    if thisNode.rrtTreeCost != thisNode.rrtLMC && Main.lessQ(thisNode, moveGoal)
+      Main.verifyInQueue(Q, thisNode)
+    end
+  end
+  ob.obstacleUnused = true
+end
+
+# ------------------------------------------------------------------ fused per-iteration query
+# One launch for what extend() asks of the geometry per sample (rrtqx.jl:926-950, DRRT_Q.jl:2551-2637):
+# nearest node, explicitNodeCheck of the sample, the shrinking-ball neighbours with their keys, and
+# explicitEdgeCheck of every new edge in both directions.  Result arrays are pinned and reused across calls; the
+# returned views are valid until the next extendQuery on the same CSpace.  julia/extend_gpu.jl is the consumer.
+function extendQuery(S, tree::GpuKDTree, point::Array{Float64}, range::Float64; capacity::Int = 8192)
+  W = world(S)
+  G = syncObstacles!(W.spheres, S)
+  if !haskey(W.pinned, :idx) || length(W.pinned[:idx]) < capacity
+    W.pinned[:idx] = pinnedVector(W.ctx, Int32, capacity); W.pinned[:dist] = pinnedVector(W.ctx, Float64, capacity)
+    W.pinned[:fwd] = pinnedVector(W.ctx, UInt8, capacity); W.pinned[:rev] = pinnedVector(W.ctx, UInt8, capacity)
+  end
+  idx = W.pinned[:idx]::Vector{Int32}; dist = W.pinned[:dist]::Vector{Float64}
+  fwd = W.pinned[:fwd]::Vector{UInt8}; rev = W.pinned[:rev]::Vector{UInt8}
+  nearestIdx = Ref{Int32}(0); nearestDist = Ref{Float64}(0.0)
+  collides = Ref{UInt8}(0); cert = Ref{Float64}(0.0); n = Ref{Int32}(0)
+  p = vec(Array{Float64}(point))
+  GC.@preserve p idx dist fwd rev check(tree.ctx, ccall((:rrtqx_extend_query, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, UInt32, Int32, Ref{Int32}, Ref{Float64}, Ref{UInt8},
+       Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}, Ptr{UInt8}),
+      tree.h, G.h, p, range, S.robotRadius, CHECK_QUICK_PASS, Int32(length(idx)), nearestIdx, nearestDist, collides, cert, n,
+      idx, dist, fwd, rev))
+  n[] <= length(idx) || return extendQuery(S, tree, point, range; capacity = 2 * Int(n[]))   # grow and repeat (rare)
+  k = min(Int(n[]), length(idx))            # never slice past the buffers
+  warm = S.inWarmupTime                     # obstacles are ignored during warm-up (DRRT_Q.jl:1805-1807, 1523-1525)
+  return (tree.nodes[nearestIdx[] + 1], nearestDist[], warm ? false : collides[] != 0, warm ? Inf : cert[],
+          view(idx, 1:k), view(dist, 1:k), warm ? falses(k) : view(fwd, 1:k) .!= 0, warm ? falses(k) : view(rev, 1:k) .!= 0)
+end
+
+# ------------------------------------------------------------------ Dubins edges (2-D polygon world)
 const DUBINS_TYPES = ("rsl", "rsr", "rlr", "lsr", "lsl", "lrl")
 
 # calculateTrajectory(S, edge::DubinsEdge) for a batch of edges (DRRT_DubinsEdge_functions.jl:329-709, space
@@ -502,15 +700,16 @@ function calculateTrajectoryBatch(ctx::Context, S, edges::Vector)
   end
 end
 
-# Dubins explicitEdgeCheck(S, edge) OR-ed over the obstacle list for a batch (DRRT_DubinsEdge_functions.jl:750-774).
-function explicitEdgeCheckBatch(G::GpuPolygons, S, edges::Vector)
+# Dubins explicitEdgeCheck OR-ed over the obstacle list of G for a batch (DRRT_DubinsEdge_functions.jl:750-774);
+# no warm-up test (the per-obstacle form of the reference has none)
+function dubinsCheck(G::GpuPolygons, S, edges::Vector)
   n = length(edges)
   starts = Matrix{Float64}(undef, 2, n); ends = Matrix{Float64}(undef, 2, n); ptr = Vector{Int64}(undef, n + 1); ptr[1] = 0
   for (i, e) in enumerate(edges)
     starts[:, i] = e.startNode.position[1:2]; ends[:, i] = e.endNode.position[1:2]
     ptr[i + 1] = ptr[i] + size(e.trajectory, 1)
   end
-  xy = Matrix{Float64}(undef, 2, ptr[end])
+  xy = Matrix{Float64}(undef, 2, ptr[n + 1])
   for (i, e) in enumerate(edges)
     xy[:, ptr[i]+1:ptr[i+1]] = permutedims(e.trajectory[:, 1:2])
   end
@@ -518,8 +717,10 @@ function explicitEdgeCheckBatch(G::GpuPolygons, S, edges::Vector)
   GC.@preserve starts ends ptr xy out check(G.ctx, ccall((:rrtqx_dubins_edge_check_batch, LIB), Int32,
       (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Int64, Float64, Float64, UInt32, Ptr{UInt8}),
       G.h, starts, ends, ptr, xy, n, S.robotRadius, S.minTurningRadius, UInt32(0), out))
-  return S.inWarmupTime ? falses(n) : out .!= 0
+  return out .!= 0
 end
+# explicitEdgeCheck(S, edge) for a batch of Dubins edges (DRRT.jl:1660-1678: false during warm-up)
+explicitEdgeCheckBatch(G::GpuPolygons, S, edges::Vector) = S.inWarmupTime ? falses(length(edges)) : dubinsCheck(G, S, edges)
 
 # saturate(newPoint, closestPoint, delta), DubinsEdge version (DRRT_DubinsEdge_functions.jl:70-95): in place.
 function saturateDubins!(ctx::Context, newPoint::Array{Float64}, closestPoint::Array{Float64}, delta::Float64)
@@ -528,5 +729,44 @@ function saturateDubins!(ctx::Context, newPoint::Array{Float64}, closestPoint::A
       (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64), ctx.h, p, c, 1, delta))
   newPoint[:] = p
 end
+
+# ------------------------------------------------------------------ hooking into the planner
+# install!() makes the planner's unqualified calls reach this module.  Call it once, after the reference's includes
+# (it refers to the reference's CSpace / Edge / SimpleEdge / DubinsEdge / rrtXQueue types in Main) and after
+# include("extend_gpu.jl") if the fused extend is wanted.  Methods that take the tree are more specific than the
+# reference's (KD::GpuKDTree) and replace nothing; methods that take only the CSpace replace the reference's methods
+# of the same signature -- from then on every CSpace must be attach!ed (there is no CPU fallback).
+function install!()
+  @eval Main begin
+    kdInsert(tree::RRTQXGpu.GpuKDTree, node) = RRTQXGpu.kdInsert(tree, node)
+    kdFindNearest(tree::RRTQXGpu.GpuKDTree, queryPoint::Array{Float64}) = RRTQXGpu.kdFindNearest(tree, queryPoint)
+    kdFindWithinRange(tree::RRTQXGpu.GpuKDTree, range::Float64, queryPoint::Array{Float64}) =
+      RRTQXGpu.kdFindWithinRange(tree, range, queryPoint)
+    kdFindMoreWithinRange(tree::RRTQXGpu.GpuKDTree, range::Float64, queryPoint::Array{Float64}, L) =
+      RRTQXGpu.kdFindMoreWithinRange(tree, range, queryPoint, L)
+    findPointsInConflictWithObstacle(S, KD::RRTQXGpu.GpuKDTree, ob, root) =
+      RRTQXGpu.findPointsInConflictWithObstacle(S, KD, ob, root)
+    addNewObstacle(S, KD::RRTQXGpu.GpuKDTree, Q, ob, root, fileCounter::Int, R) =
+      RRTQXGpu.addNewObstacle(S, KD, Q, ob, root, fileCounter, R)
+    removeObstacle(S, KD::RRTQXGpu.GpuKDTree, Q, ob, root, hyberBallRad::Float64, timeElapsed::Float64, moveGoal) =
+      RRTQXGpu.removeObstacle(S, KD, Q, ob, root, hyberBallRad, timeElapsed, moveGoal)
+    # replaced: same signatures as DRRT_Q.jl:1802,1520,1558,1594,1595 and the per-edge-type methods
+    explicitEdgeCheck(C::CSpace{T}, edge::Edge) where {T} = RRTQXGpu.explicitEdgeCheck(C, edge)
+    explicitEdgeCheck(S::CSpace{T}, edge::Edge, obstacle::OT) where {T, OT} = RRTQXGpu.explicitEdgeCheck(S, edge, obstacle)
+    explicitPointCheck(S::CSpace{T}, point::Array{Float64}) where {T} = RRTQXGpu.explicitPointCheck(S, point)
+    explicitPointCheck3D(S::CSpace{T}, point::Array{Float64}) where {T} = RRTQXGpu.explicitPointCheck3D(S, point)
+    explicitNodeCheck(S::CSpace{T}, node) where {T} = RRTQXGpu.explicitNodeCheck(S, node)
+    explicitNodeCheck3D(S::CSpace{T}, node) where {T} = RRTQXGpu.explicitNodeCheck3D(S, node)
+  end
+  if isdefined(RRTQXGpu, :extendRRTx)
+    @eval Main begin
+      extend(S, KD::RRTQXGpu.GpuKDTree, Q::rrtXQueue, newNode, closestNode, delta::Float64, hyberBallRad::Float64, moveGoal) =
+        RRTQXGpu.extendRRTx(S, KD, Q, newNode, closestNode, delta, hyberBallRad, moveGoal)
+    end
+  end
+  return nothing
+end
+
+isfile(joinpath(@__DIR__, "extend_gpu.jl")) && include("extend_gpu.jl")
 
 end # module

@@ -33,6 +33,8 @@ SIGNATURES = {
     "rrtqx_ctx_destroy": (i32, [vp]),
     "rrtqx_last_error": (C.c_char_p, [vp]),
     "rrtqx_ctx_reload_tuning": (i32, [vp]),
+    "rrtqx_host_alloc": (i32, [vp, i64, C.POINTER(vp)]),
+    "rrtqx_host_free": (i32, [vp, vp]),
     "rrtqx_ctx_sync": (i32, [vp]),
     "rrtqx_ctx_kernel_launches": (i32, [vp, C.POINTER(i64)]),
     "rrtqx_ctx_last_phase_ms": (i32, [vp, C.c_char_p, C.POINTER(C.c_float)]),

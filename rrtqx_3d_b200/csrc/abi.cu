@@ -116,6 +116,31 @@ rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx) {
   });
 }
 
+// Page-locked host memory for the caller's query / result arrays: the library accepts any host pointer, but
+// copies from pageable memory are staged by the driver at a fraction of the PCIe rate.
+rrtqx_status rrtqx_host_alloc(rrtqx_ctx *ctx, int64_t bytes, void **out) {
+  if (!ctx || !out) return RRTQX_ERR_INVALID;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    RQ_REQUIRE(bytes >= 0, "bytes is negative");
+    *out = nullptr;
+    if (bytes == 0) return;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); throw Error(RRTQX_ERR_NOMEM, std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e)); }
+  });
+}
+
+rrtqx_status rrtqx_host_free(rrtqx_ctx *ctx, void *p) {
+  if (!p) return RRTQX_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (ctx && handle_live(ctx)) ctx->err = std::string("cudaFreeHost failed: ") + cudaGetErrorString(e);
+    return RRTQX_ERR_INVALID;
+  }
+  return RRTQX_OK;
+}
+
 rrtqx_status rrtqx_ctx_reload_tuning(rrtqx_ctx *ctx) {
   if (!ctx) return RRTQX_ERR_INVALID;
   ctx->tune.load();

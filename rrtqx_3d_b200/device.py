@@ -37,6 +37,20 @@ class Context:
     def sync(self):
         A.check(self.L.rrtqx_ctx_sync(self.h), self.h)
 
+    def host_array(self, shape, dtype):
+        """A numpy array over page-locked host memory from rrtqx_host_alloc (freed when the array's owner dies)."""
+        shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = A.vp()
+        A.check(self.L.rrtqx_host_alloc(self.h, max(nbytes, 1), C.byref(p)), self.h)
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        L, addr = self.L, p.value
+        import weakref
+        weakref.finalize(buf, lambda: L.rrtqx_host_free(None, addr))
+        return arr
+
     def reload_tuning(self):
         """Re-read the diagnostic RRTQX_* environment switches (they are otherwise read once, at creation)."""
         A.check(self.L.rrtqx_ctx_reload_tuning(self.h), self.h)
