@@ -503,6 +503,66 @@ RRTQX_API rrtqx_status rrtqx_dubins_saturate_batch(rrtqx_ctx *ctx,
                                                    const double *closest,
                                                    int64_t n, double delta);
 
+/* ------------------------------------------------------------ multi-GPU */
+/* The path shards embarrassingly: tree and obstacles are
+ * replicated per GPU, rank g owns a contiguous slice of a batch, and the only
+ * exchange is the gather of fixed-size results.  A communicator spans the
+ * ranks of the job; this process drives n_local of them:
+ *   rrtqx_comm_init_local -- ONE process holding one context per device (what
+ *     a Julia host does; the reference is one process, rrtqx.jl:331).  When all
+ *     devices have peer access the flag gather of the sharded check is fused
+ *     into its packing kernel (direct stores into the peers' buffers over
+ *     NVLink), otherwise NCCL gathers.
+ *   rrtqx_comm_init_rank  -- one process per GPU (torchrun): every rank passes
+ *     the 128-byte id rank 0 obtained from rrtqx_comm_unique_id (moved between
+ *     the processes by the caller), its rank and the rank count.  NCCL gathers.
+ * NCCL (libnccl.so.2) is loaded on first use; without it these calls fail with
+ * RRTQX_ERR_UNSUPPORTED and nothing else is affected. */
+typedef struct rrtqx_comm rrtqx_comm;
+RRTQX_API rrtqx_status rrtqx_comm_init_local(rrtqx_ctx *const *ctxs, int32_t n,
+                                             rrtqx_comm **out);
+RRTQX_API rrtqx_status rrtqx_comm_unique_id(void *id128);
+RRTQX_API rrtqx_status rrtqx_comm_init_rank(rrtqx_ctx *ctx, const void *id128,
+                                            int32_t rank, int32_t n_ranks,
+                                            rrtqx_comm **out);
+RRTQX_API rrtqx_status rrtqx_comm_destroy(rrtqx_comm *comm);
+/* any output pointer may be NULL.  peer_stores = 1: the fused store path is
+ * active.  nccl_version: NCCL_VERSION_CODE of the loaded library (0 when the
+ * communicator has one rank and NCCL was never loaded). */
+RRTQX_API rrtqx_status rrtqx_comm_info(const rrtqx_comm *comm, int32_t *n_ranks,
+                                       int32_t *n_local, int32_t *first_rank,
+                                       int32_t *peer_stores,
+                                       int32_t *nccl_version);
+/* All-gather of bytes_per_rank bytes per rank (fixed-size results: per-query
+ * counts, nearest idx/dist): send[i] / recv[i] are device pointers of local
+ * rank i, recv holds n_ranks * bytes_per_rank bytes in rank order.  Queued on
+ * the contexts' streams, or (on_side_stream != 0) on the communicator's side
+ * streams behind what the main streams hold so far, so that the next step does
+ * not wait for it; rrtqx_comm_join makes the main streams wait for every
+ * gather queued that way.  Asynchronous: synchronise the contexts to read. */
+RRTQX_API rrtqx_status rrtqx_comm_allgather(rrtqx_comm *comm,
+                                            const void *const *send,
+                                            void *const *recv,
+                                            int64_t bytes_per_rank,
+                                            int32_t on_side_stream);
+RRTQX_API rrtqx_status rrtqx_comm_join(rrtqx_comm *comm);
+/* explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826) for ONE edge batch sharded
+ * over the ranks: every rank holds the same device-resident edge list
+ * (src[i] / dst[i], n_edges entries) next to its replica of the tree and the
+ * obstacles; rank g checks the edges of word shard g and every rank ends up
+ * with ALL flags, bit-packed: edge e is bit (e % 32) of word e / 32 of
+ * packed_out[i] (device, rrtqx_comm_packed_words() words: G equal shards).
+ * Blocking. */
+RRTQX_API rrtqx_status rrtqx_comm_packed_words(const rrtqx_comm *comm,
+                                               int64_t n_edges,
+                                               int64_t *words_total,
+                                               int64_t *words_per_rank);
+RRTQX_API rrtqx_status rrtqx_edge_check_batch_sharded(
+    rrtqx_comm *comm, rrtqx_tree *const *trees,
+    const rrtqx_spheres *const *spheres, const int32_t *const *src,
+    const int32_t *const *dst, int64_t n_edges, double robot_radius,
+    uint32_t flags, uint32_t *const *packed_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,15 @@ SIGNATURES = {
     "rrtqx_edges_set_parents": (i32, [vp, vp, vp, i64]),
     "rrtqx_obstacle_add_sweep": (i32, [vp, vp, vp, i64, f64, f64, u32, C.POINTER(vp)]),
     "rrtqx_obstacle_remove_sweep": (i32, [vp, vp, i32, vp, i64, vp, f64, f64, u32, C.POINTER(vp)]),
+    "rrtqx_comm_init_local": (i32, [vp, i32, C.POINTER(vp)]),
+    "rrtqx_comm_unique_id": (i32, [vp]),
+    "rrtqx_comm_init_rank": (i32, [vp, vp, i32, i32, C.POINTER(vp)]),
+    "rrtqx_comm_destroy": (i32, [vp]),
+    "rrtqx_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "rrtqx_comm_allgather": (i32, [vp, vp, vp, i64, i32]),
+    "rrtqx_comm_join": (i32, [vp]),
+    "rrtqx_comm_packed_words": (i32, [vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+    "rrtqx_edge_check_batch_sharded": (i32, [vp, vp, vp, vp, vp, i64, f64, u32, vp]),
     "rrtqx_edges_set_trajectories": (i32, [vp, vp, vp]),
     "rrtqx_edges_solve_trajectories": (i32, [vp, f64, C.POINTER(i64)]),
     "rrtqx_edges_trajectories_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),

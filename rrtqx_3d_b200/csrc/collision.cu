@@ -243,9 +243,14 @@ edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ s
   if (valid) out[e] = hit ? 1 : 0;
 }
 
-void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
-                const int32_t *dst, const double *starts, const double *ends, int64_t n_edges, double robot_radius,
-                uint32_t flags, uint8_t *collide_out) {
+// Everything of the batched check except the final synchronisation: kernels and the copy of the flags to a host
+// destination are queued on the context's stream; *bad_dev (if not NULL) receives the device counter of
+// out-of-range endpoints (valid when the tree path ran, else NULL).  The sharded multi-GPU form queues this on
+// every device before it waits for any of them.
+void edge_check_launch(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                       const int32_t *dst, const double *starts, const double *ends, int64_t n_edges,
+                       double robot_radius, uint32_t flags, uint8_t *collide_out, const int32_t **bad_dev) {
+  if (bad_dev) *bad_dev = nullptr;
   if (n_edges <= 0) return;
   cudaStream_t st = ctx->stream;
   const bool from_tree = tree != nullptr;
@@ -329,9 +334,18 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
     }
   }
   if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n_edges);
+  if (bad_dev && from_tree) *bad_dev = dbad;
+}
+
+void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                const int32_t *dst, const double *starts, const double *ends, int64_t n_edges, double robot_radius,
+                uint32_t flags, uint8_t *collide_out) {
+  if (n_edges <= 0) return;
+  const int32_t *dbad = nullptr;
+  edge_check_launch(ctx, tree, spheres, src, dst, starts, ends, n_edges, robot_radius, flags, collide_out, &dbad);
   int32_t n_bad = 0;
-  if (from_tree) RQ_CUDA(cudaMemcpyAsync(&n_bad, dbad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  RQ_CUDA(cudaStreamSynchronize(st));
+  if (dbad) RQ_CUDA(cudaMemcpyAsync(&n_bad, dbad, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  RQ_CUDA(cudaStreamSynchronize(ctx->stream));
   RQ_REQUIRE(n_bad == 0, "edge endpoint out of range");
 }
 

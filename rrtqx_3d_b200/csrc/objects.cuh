@@ -88,6 +88,9 @@ void extend_query(rrtqx_tree *t, const rrtqx_spheres *S, const double *point, do
 void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
                 const int32_t *dst, const double *starts, const double *ends, int64_t n_edges, double robot_radius,
                 uint32_t flags, uint8_t *collide_out);
+void edge_check_launch(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *spheres, const int32_t *src,
+                       const int32_t *dst, const double *starts, const double *ends, int64_t n_edges,
+                       double robot_radius, uint32_t flags, uint8_t *collide_out, const int32_t **bad_dev);
 void node_check(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *points, int64_t n, double robot_radius,
                 uint32_t flags, uint8_t *collide_out, double *cert_out);
 // sweep.cu

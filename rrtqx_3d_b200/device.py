@@ -615,3 +615,82 @@ def dubins_saturate_batch(ctx: Context, new_points, closest, delta):
     cl = A.as_f64(closest, 4)
     A.check(ctx.L.rrtqx_dubins_saturate_batch(ctx.h, A.ptr(pts), A.ptr(cl), pts.shape[0], float(delta)), ctx.h)
     return pts
+
+
+class Comm:
+    """rrtqx_comm: the ranks of a sharded job.  Comm.local(ctxs): ONE process driving one context per device (the
+    reference's host is one process); Comm.rank(ctx, id, rank, n): one process per GPU (torchrun), `id` being the
+    128 bytes rank 0 got from Comm.unique_id() and handed to the others."""
+
+    def __init__(self, h, ctxs):
+        self.h, self.ctxs, self.L = h, list(ctxs), ctxs[0].L
+
+    @classmethod
+    def local(cls, ctxs):
+        arr = (A.vp * len(ctxs))(*[c.h for c in ctxs])
+        h = A.vp()
+        A.check(ctxs[0].L.rrtqx_comm_init_local(arr, len(ctxs), C.byref(h)), ctxs[0].h)
+        return cls(h, ctxs)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        A.check(A.lib().rrtqx_comm_unique_id(buf), None)
+        return buf.raw
+
+    @classmethod
+    def rank(cls, ctx, unique_id: bytes, rank: int, n_ranks: int):
+        h = A.vp()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        A.check(ctx.L.rrtqx_comm_init_rank(ctx.h, buf, int(rank), int(n_ranks), C.byref(h)), ctx.h)
+        return cls(h, [ctx])
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrtqx_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        v = [A.i32(0) for _ in range(5)]
+        A.check(self.L.rrtqx_comm_info(self.h, *[C.byref(x) for x in v]), self.ctxs[0].h)
+        return {"n_ranks": v[0].value, "n_local": v[1].value, "first_rank": v[2].value,
+                "peer_stores": bool(v[3].value), "nccl_version": v[4].value}
+
+    def packed_words(self, n_edges: int):
+        a, b = A.i64(0), A.i64(0)
+        A.check(self.L.rrtqx_comm_packed_words(self.h, int(n_edges), C.byref(a), C.byref(b)), self.ctxs[0].h)
+        return int(a.value), int(b.value)
+
+    def allgather(self, send_ptrs, recv_ptrs, bytes_per_rank: int, side_stream: bool = False):
+        """send_ptrs / recv_ptrs: one device pointer per local rank."""
+        n = len(self.ctxs)
+        s = (A.vp * n)(*[A.ptr(p) for p in send_ptrs])
+        r = (A.vp * n)(*[A.ptr(p) for p in recv_ptrs])
+        A.check(self.L.rrtqx_comm_allgather(self.h, s, r, int(bytes_per_rank), 1 if side_stream else 0), self.ctxs[0].h)
+
+    def join(self):
+        A.check(self.L.rrtqx_comm_join(self.h), self.ctxs[0].h)
+
+    def edge_check_sharded(self, trees, spheres, src_ptrs, dst_ptrs, n_edges, robot_radius, packed_ptrs, flags=0):
+        """explicitEdgeCheck of one replicated edge list, sharded over the ranks; every rank's packed_ptrs[i] (device,
+        packed_words(n_edges)[0] uint32 words) receives ALL flags: edge e = bit e % 32 of word e // 32."""
+        n = len(self.ctxs)
+        t = (A.vp * n)(*[x.h for x in trees])
+        sp = (A.vp * n)(*[x.h for x in spheres])
+        s = (A.vp * n)(*[A.ptr(p) for p in src_ptrs])
+        d = (A.vp * n)(*[A.ptr(p) for p in dst_ptrs])
+        o = (A.vp * n)(*[A.ptr(p) for p in packed_ptrs])
+        A.check(self.L.rrtqx_edge_check_batch_sharded(self.h, t, sp, s, d, int(n_edges), float(robot_radius), int(flags), o),
+                self.ctxs[0].h)
+
+
+def unpack_flags(words, n_edges: int) -> np.ndarray:
+    """Bit-packed flags of Comm.edge_check_sharded (host uint32 array) -> uint8[n_edges]."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    return np.unpackbits(w.view(np.uint8), bitorder="little")[:n_edges]
