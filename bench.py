@@ -451,7 +451,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rrtqx_3d_b200.device import Context, DeviceTree, EdgeSet, RangeResult, SphereSet, SweepResult
+    from rrtqx_3d_b200.device import Comm, Context, DeviceTree, EdgeSet, RangeResult, SphereSet, SweepResult
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -459,6 +459,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream.cuda_stream)
+    comm = None
+    if world > 1:   # the library's own communicator (NCCL inside librrtqx_b200.so); torch only moves the unique id
+        uid = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = Comm.rank(ctx, uid[0], rank, world)
     peak_gbs, peak_src = measured_peaks()
 
     # ------------------------------------------------------------- workload C2
@@ -477,12 +482,9 @@ def main():
 
     def step():
         _, total = tree.range_query(dq, r, want_dist=True, result=res, n_queries=args.queries)
-        if world > 1:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink)
-            cptr = res.device_pointers()[0]
-            if cptr not in counts_view:      # the library's buffers are grow-only: the view is built once
-                counts_view.clear()
-                counts_view[cptr] = tensor_from_ptr(torch, cptr, args.queries, torch.int32)
-            dist.all_gather_into_tensor(gathered, counts_view[cptr])
+        if world > 1:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink, inside the
+            # library, on its side stream: the next step's kernel does not wait for it)
+            comm.allgather([res.device_pointers()[0]], [gathered.data_ptr()], args.queries * 4, side_stream=True)
         return total
 
     def tensor_from_ptr(torch_mod, p, n, dtype):
@@ -518,13 +520,20 @@ def main():
                 kern[k].append(ctx.last_phase_ms(k))
             except Exception:
                 pass
+    tail_ms = 0.0
+    if world > 1:   # the gathers still in flight on the side stream belong to the timed steps: wait for them
+        t_end = torch.cuda.Event(enable_timing=True)
+        comm.join()
+        t_end.record(stream)
+        torch.cuda.synchronize()
+        tail_ms = ev[-1][1].elapsed_time(t_end)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     launches = ctx.kernel_launches() - launches0
-    ms_local = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    ms_local = float(np.mean([a.elapsed_time(b) for a, b in ev])) + tail_ms / max(1, len(ev))
     if world > 1:
         tmax = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -561,7 +570,9 @@ def main():
                                    "shrinking-ball radius, idx + distance keys",
                        "nodes": args.nodes, "queries_per_gpu": args.queries, "radius": r,
                        "neighbours_per_step_rank0": K, "mean_neighbours": K / args.queries,
-                       "parallelism": f"replicated tree x {world} query shards", "l2_flush_between_steps": True},
+                       "parallelism": f"replicated tree x {world} query shards", "l2_flush_between_steps": True,
+                       "count_gather": ("rrtqx_comm_allgather (NCCL inside the library) on the communicator's side stream; "
+                                        "the timed steps include the wait for the last gather") if world > 1 else "none (one rank)"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps}
 
@@ -769,21 +780,18 @@ def main():
             src, dst, _ = build_c3_edges(tree, pts, args.sweep_edge_radius)     # every rank: same edge set
             centers, radii = W.c3_obstacles(args.sweep_obstacles)
             S5 = SphereSet(ctx, centers, radii)
-            lo, hi = shard_bounds(len(src), rank, world)
-            per = (len(src) + world - 1) // world
-            dsrc, ddst = torch.from_numpy(src[lo:hi]).cuda(), torch.from_numpy(dst[lo:hi]).cuda()
-            dflag = torch.zeros(per, dtype=torch.uint8, device="cuda")           # padded to a common shard size
-            allflags = torch.empty(per * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+            c5comm = comm if comm is not None else Comm.local([ctx])
+            words, _ = c5comm.packed_words(len(src))
+            dsrc, ddst = torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda()   # replicated edge list
+            packed = torch.zeros(words, dtype=torch.int32, device="cuda")             # ALL flags, bit-packed, on every rank
+            torch.cuda.synchronize()
             evs = []
             for it in range(3 + args.steps):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                if world > 1:
-                    dist.barrier()
                 a.record(stream)
-                edge_check_batch(tree, S5, dsrc, ddst, W.ROBOT_RADIUS, n_edges=hi - lo, out=dflag)
-                if world > 1:   # the only exchange of the path: gather the sharded flags (NCCL)
-                    dist.all_gather_into_tensor(allflags, dflag)
+                # rank g checks word shard g; the packed words are gathered inside the library (NCCL, in place)
+                c5comm.edge_check_sharded([tree], [S5], [dsrc], [ddst], len(src), W.ROBOT_RADIUS, [packed])
                 b.record(stream)
                 b.synchronize()
                 if it >= 3:
@@ -797,11 +805,15 @@ def main():
                 dd = torch.tensor([done], device="cuda", dtype=torch.int64)
                 dist.all_reduce(dd)
                 done = int(dd.item())
-                colliding = int(allflags.view(world, per)[:, :].sum().item())
-            else:
-                colliding = int(dflag.sum().item())
+            pk = packed.cpu().numpy().view(np.uint32)
+            colliding = int(np.unpackbits(pk.view(np.uint8))[:].sum())   # padding words are zero
+            c5_info = c5comm.info()
+            if comm is None:
+                c5comm.close()
             line["c5"] = {"workload": "C5: C3 edge set sharded contiguously over the ranks (tree + 256 spheres replicated, "
-                                      "flags all-gathered over NCCL) and independent C1-style planning instances round-robin",
+                                      "bit-packed flags gathered inside the library: rrtqx_edge_check_batch_sharded) and "
+                                      "independent C1-style planning instances round-robin",
+                          "comm": c5_info,
                           "edges": len(src), "edge_shards": world, "edge_batch_ms": ems,
                           "edges_per_s": len(src) / (ems / 1e3), "colliding_edges": colliding, "scaling": "strong",
                           "instances": args.c5_instances, "iterations_per_instance": args.c5_iterations,
