@@ -721,6 +721,16 @@ def main():
                 if it >= 3:
                     et.append(ctx.last_phase_ms("edge_check"))
             ems = float(np.mean(et))
+            # the same check over the RESIDENT edge set (rrtqx_edges_check_batch: per-edge records prepared at upload)
+            rflag = torch.empty(len(src), dtype=torch.uint8, device="cuda")
+            rt = []
+            for it in range(3 + args.steps):
+                flush.zero_()
+                E.check_all(S, W.ROBOT_RADIUS, out=rflag.data_ptr())
+                if it >= 3:
+                    rt.append(ctx.last_phase_ms("edges_check"))
+            rms = float(np.mean(rt))
+            resident_equal = bool(torch.equal(rflag, dflag))
             # CPU side of the same batch: the oracle's explicitEdgeCheck loop (front-to-back over the obstacle list,
             # early exit) on a bounded sample of the edges, all host threads
             cpu_edge = None
@@ -746,6 +756,10 @@ def main():
             line["edge_batch"] = {"cpu_baseline": cpu_edge,
                                   "workload": "explicitEdgeCheck(S, edge) for every C3 edge against all 256 spheres (device-resident)",
                                   "edges": len(src), "obstacles": args.sweep_obstacles, "ms": ems,
+                                  "resident_ms": rms, "resident_edges_per_s": len(src) / (rms / 1e3),
+                                  "resident_equals_batch": resident_equal,
+                                  "resident_algorithmic_bytes": len(src) * 17,
+                                  "resident_hbm_frac": len(src) * 17 / (rms / 1e3) / 1e9 / peak_gbs,
                                   "edges_per_s": len(src) / (ems / 1e3),
                                   "edge_obstacle_pairs_per_s": len(src) * args.sweep_obstacles / (ems / 1e3),
                                   "colliding_edges": int(dflag.sum().item()),

@@ -314,6 +314,16 @@ RRTQX_API rrtqx_status rrtqx_edges_set_parents(rrtqx_edges *e,
                                                const int32_t *parent_ids,
                                                int64_t n);
 RRTQX_API rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges);
+/* explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826) of EVERY resident out-edge:
+ * collide_out[e] for edge id e (n_edges entries, host or device).  Same
+ * result as rrtqx_edge_check_batch on the same (src, dst) pairs; the resident
+ * form streams per-edge records prepared when the set was built instead of
+ * gathering the end points of every edge on every call. */
+RRTQX_API rrtqx_status rrtqx_edges_check_batch(rrtqx_edges *e,
+                                               const rrtqx_spheres *spheres,
+                                               double robot_radius,
+                                               uint32_t flags,
+                                               uint8_t *collide_out);
 
 /* addNewObstacle (DRRT_Q.jl:3220-3290) geometric part, batched over obstacles
  * ob_ids[0..n_obs) of `spheres` (treated as active, :3222).  For obstacle o:

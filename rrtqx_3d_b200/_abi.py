@@ -70,6 +70,7 @@ SIGNATURES = {
     "rrtqx_edges_destroy": (i32, [vp]),
     "rrtqx_edges_upload": (i32, [vp, vp, vp, i64, vp, i64]),
     "rrtqx_edges_size": (i32, [vp, C.POINTER(i64)]),
+    "rrtqx_edges_check_batch": (i32, [vp, vp, f64, u32, vp]),
     "rrtqx_edges_append": (i32, [vp, vp, vp, i64]),
     "rrtqx_edges_set_parents": (i32, [vp, vp, vp, i64]),
     "rrtqx_obstacle_add_sweep": (i32, [vp, vp, vp, i64, f64, f64, u32, C.POINTER(vp)]),

@@ -639,6 +639,16 @@ rrtqx_status rrtqx_edges_set_parents(rrtqx_edges *e, const int32_t *node_ids, co
   });
 }
 
+rrtqx_status rrtqx_edges_check_batch(rrtqx_edges *e, const rrtqx_spheres *spheres, double robot_radius, uint32_t flags,
+                                     uint8_t *collide_out) {
+  if (!e || !spheres) return RRTQX_ERR_INVALID;
+  rrtqx_ctx *ctx = e->tree->ctx;
+  return guarded(ctx, [&] {
+    bind_device(ctx);
+    edges_check(e, spheres, robot_radius, flags, collide_out);
+  });
+}
+
 rrtqx_status rrtqx_edges_size(const rrtqx_edges *e, int64_t *n_edges) {
   if (!e || !n_edges) return RRTQX_ERR_INVALID;
   *n_edges = e->n_edges;

@@ -121,12 +121,70 @@ static inline int64_t cover_min_items(const rrtqx_ctx *ctx, int64_t dflt) {
   return ctx->tune.cover_min_items >= 0 ? ctx->tune.cover_min_items : dflt;
 }
 
+// ---------------------------------------------------------------- per-item records of a resident edge set
+// Built once per edge-set (re)build, in item order (out-edges in upload order, then one parent edge per node):
+//   frec  = (fl32(mid.x), fl32(mid.y), fl32(mid.z), h)   h = FP32 upper bound of half the edge length;
+//           h = -1: the item has no edge (node without parent); h = +inf: degenerate edge (zero length or non-finite
+//           ends: the reference collides it with every active obstacle) -> decided by the slow kernel
+//   exact = start.xyz, end.xyz as six doubles (three 16-byte loads)
+// so the collect stage streams 16 bytes per item and never touches the node table, and the test stage reads the end
+// points of the surviving pairs from consecutive records (pairs are listed in item order) instead of two random
+// 32-byte gathers per pair.
+struct ItemRecords {
+  const float4 *frec;
+  const double2 *exact;  // 3 per item
+};
+
+static __global__ void __launch_bounds__(256)
+item_records_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src,
+                    const int32_t *__restrict__ dst, int64_t n_edges, const int32_t *__restrict__ parent,
+                    float4 *__restrict__ frec, double2 *__restrict__ exact) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_edges + n_nodes) return;
+  int v, w;
+  if (i >= n_edges) {
+    v = (int)(i - n_edges);
+    w = parent ? parent[v] : -1;
+  } else {
+    v = src[i];
+    w = dst[i];
+  }
+  if (w < 0) {
+    frec[i] = make_float4(0.f, 0.f, 0.f, -1.f);
+    exact[3 * i] = exact[3 * i + 1] = exact[3 * i + 2] = make_double2(0.0, 0.0);
+    return;
+  }
+  const double4 a = pos[v], b = pos[w];
+  exact[3 * i] = make_double2(a.x, a.y);
+  exact[3 * i + 1] = make_double2(a.z, b.x);
+  exact[3 * i + 2] = make_double2(b.y, b.z);
+  // the same quantities pq_collect_kernel derives from gathered end points
+  const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y), dz = __dsub_rn(a.z, b.z);
+  const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y), mz = 0.5 * (a.z + b.z);
+  float h;
+  if (!(s2 > 0.0) || !isfinite(s2) || !isfinite(mx + my + mz)) {
+    h = INFINITY;
+  } else {
+    float rt;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(__double2float_ru(s2)));
+    h = 0.5f * (rt * 1.000001f) + 1e-19f;  // >= len / 2
+  }
+  frec[i] = make_float4(__double2float_rn(mx), __double2float_rn(my), __double2float_rn(mz), h);
+}
+
 // ---------------------------------------------------------------- pair queue
 constexpr int PQ_THREADS = 128;  // collect kernel block
 constexpr int PQ_KEEP = 4;       // pairs an item may put on the list; items with more go to the slow list
 constexpr unsigned PQ_NONE = 0xffffffffu;  // filler pair (skipped by the test kernel)
 
 // Src supplies the items:
+//   static constexpr bool RESIDENT                                   true: per-item records were prepared when the edge
+//                                                                    set was built (ItemRecords below): stage 1 streams
+//                                                                    ONE coalesced 16-byte FP32 record per item instead
+//                                                                    of gathering two node positions, and stage 2 reads
+//                                                                    the exact end points from the item's own record
+//   float4 frec(int64_t i)                                           (RESIDENT) FP32 record of item i
 //   bool endpoints(int64_t i, double a[3], double b[3], int &v)   false: item has no edge (node without parent)
 //   void clear(int64_t i)                                           before any test of item i
 //   bool accept(int o, const double4 &rec, const double a[3], int v)  extra condition on a colliding pair
@@ -159,25 +217,53 @@ pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const
   {
     double a[3], b[3];
     int v;
-    if (i < n_items && S.endpoints(i, a, b, v)) {
-      S.clear(i);
-      // the invariants this stage needs, without the FP64 sqrt: squared length, midpoint, and an FP32 upper
-      // bound of the half length.  s is the reference's radicand (same operations as seg_prepare), so
-      // s == 0 / non-finite is exactly len == 0 / non-finite.
-      const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
-      const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      const double mx = 0.5 * (a[0] + b[0]), my = 0.5 * (a[1] + b[1]), mz = 0.5 * (a[2] + b[2]);
-      if (!(s2 > 0.0) || !isfinite(s2) || !isfinite(mx + my + mz)) {
+    // item invariants of this stage: midpoint (FP64 for the cell look-ups, FP32 for the reject), an FP32 upper
+    // bound of the half length, and "degenerate" (no reject possible)
+    bool have = false, degenerate = false;
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    SegF32 sf;
+    sf.mx = sf.my = sf.mz = sf.half = sf.bound = 0.f;
+    sf.ok = false;
+    if constexpr (Src::RESIDENT) {
+      if (i < n_items) {
+        const float4 fr = S.frec(i);      // ONE coalesced 16-byte load per item
+        if (fr.w >= 0.f) {
+          have = true;
+          S.clear(i);
+          degenerate = !(fr.w < INFINITY);
+          sf.mx = fr.x; sf.my = fr.y; sf.mz = fr.z; sf.half = fr.w;
+          mx = fr.x; my = fr.y; mz = fr.z;   // the FP32 midpoint picks the cells; its error goes into the margins below
+        }
+      }
+    } else {
+      if (i < n_items && S.endpoints(i, a, b, v)) {
+        have = true;
+        S.clear(i);
+        // squared length as the reference's radicand (same operations as seg_prepare), so s2 == 0 / non-finite is
+        // exactly len == 0 / non-finite; no FP64 sqrt: sqrt.approx upper bound
+        const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
+        const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        mx = 0.5 * (a[0] + b[0]); my = 0.5 * (a[1] + b[1]); mz = 0.5 * (a[2] + b[2]);
+        degenerate = !(s2 > 0.0) || !isfinite(s2) || !isfinite(mx + my + mz);
+        if (!degenerate) {
+          sf.mx = __double2float_rn(mx); sf.my = __double2float_rn(my); sf.mz = __double2float_rn(mz);
+          float rt;  // sqrt.approx: 1 ulp-level error, covered by the 1e-6 factor; + 1e-19 for flushed subnormals
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(__double2float_ru(s2)));
+          sf.half = 0.5f * (rt * 1.000001f) + 1e-19f;  // >= len / 2
+        }
+      }
+    }
+    if (have) {
+      if (degenerate) {
         to_slow = heavy = true;  // degenerate (or undecidable here): the slow kernel works it out exactly
       } else {
-        SegF32 sf;
-        sf.mx = __double2float_rn(mx); sf.my = __double2float_rn(my); sf.mz = __double2float_rn(mz);
-        float rt;  // sqrt.approx: 1 ulp-level error, covered by the 1e-6 factor; + 1e-19 for flushed subnormals
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(__double2float_ru(s2)));
-        sf.half = 0.5f * (rt * 1.000001f) + 1e-19f;  // >= len / 2
         sf.bound = 3.0e-7f * (G.cmax + fmaxf(fabsf(sf.mx), fmaxf(fabsf(sf.my), fabsf(sf.mz))));
         sf.ok = isfinite(sf.bound) && isfinite(sf.half);
-        heavy = !(G.cov_on && s2 <= G.cov_len2);
+        // cover lists serve edges with half length <= cov_cap.  RESIDENT: the midpoint used for the cell look-up is the
+        // FP32 one, up to sf.bound / 3 away from the true midpoint per coordinate: that slack is part of cov_margin
+        // only for the FP64 midpoint, so it is charged against the half length here.
+        const float half_eff = Src::RESIDENT ? sf.half + sf.bound : sf.half;
+        heavy = !(G.cov_on && (double)half_eff * (1.0 + 1e-6) <= G.cov_cap);
         auto visit = [&](int o, const float4 f) {
           if (seg_reject_f32(sf, f)) return;
           if (nk < PQ_KEEP) keep[nk][threadIdx.x] = o;
@@ -195,7 +281,7 @@ pq_collect_kernel(Src S, int64_t n_items, const float4 *__restrict__ frec, const
             visit((int)(w & 0xffffu), f);
           }
         } else {
-          const double R = (0.5 * __dsqrt_ru(s2) + G.thr_max) * (1.0 + 1e-9) + 1e-300;
+          const double R = ((double)half_eff + G.thr_max) * (1.0 + 1e-6) + 1e-300;  // half_eff >= len / 2 (+ midpoint slack)
           const int x0 = sg_cell(mx - R, G.lo[0], G.inv[0], G.nx), x1 = sg_cell(mx + R, G.lo[0], G.inv[0], G.nx);
           const int y0 = sg_cell(my - R, G.lo[1], G.inv[1], G.ny), y1 = sg_cell(my + R, G.lo[1], G.inv[1], G.ny);
           const int z0 = sg_cell(mz - R, G.lo[2], G.inv[2], G.nz), z1 = sg_cell(mz + R, G.lo[2], G.inv[2], G.nz);

@@ -160,6 +160,8 @@ edge_check_grid_kernel(const double4 *__restrict__ pos, const int32_t *__restric
 // Item source of the two-stage form of the same check (collide_queue.cuh).
 template <bool SRC_TREE>
 struct BatchEdgeSrc {
+  static constexpr bool RESIDENT = false;   // end points are gathered per call (no prepared item records)
+  __device__ __forceinline__ float4 frec(int64_t) const { return make_float4(0.f, 0.f, 0.f, -1.f); }
   const double4 *pos;
   const int32_t *src, *dst;
   const double *starts, *ends;
@@ -183,6 +185,24 @@ struct BatchEdgeSrc {
       a[0] = pa[0]; a[1] = pa[1]; a[2] = pa[2];
       b[0] = pb[0]; b[1] = pb[1]; b[2] = pb[2];
     }
+    return true;
+  }
+  __device__ __forceinline__ void clear(int64_t i) const { out[i] = 0; }
+  __device__ __forceinline__ bool accept(int, const double4 &, const double *, int) const { return true; }
+  __device__ __forceinline__ void mark(int64_t i) const { out[i] = 1; }
+};
+
+// Resident form: every out-edge of an rrtqx_edges set, item records prepared when the set was built.
+struct ResidentEdgeSrc {
+  static constexpr bool RESIDENT = true;
+  ItemRecords rec;
+  uint8_t *out;
+  __device__ __forceinline__ float4 frec(int64_t i) const { return rec.frec[i]; }
+  __device__ __forceinline__ bool endpoints(int64_t i, double a[3], double b[3], int &v) const {
+    const double2 p0 = rec.exact[3 * i], p1 = rec.exact[3 * i + 1], p2 = rec.exact[3 * i + 2];
+    a[0] = p0.x; a[1] = p0.y; a[2] = p1.x;
+    b[0] = p1.y; b[1] = p2.x; b[2] = p2.y;
+    v = 0;
     return true;
   }
   __device__ __forceinline__ void clear(int64_t i) const { out[i] = 0; }
@@ -347,6 +367,53 @@ void edge_check(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spheres *sph
   if (dbad) RQ_CUDA(cudaMemcpyAsync(&n_bad, dbad, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   RQ_CUDA(cudaStreamSynchronize(ctx->stream));
   RQ_REQUIRE(n_bad == 0, "edge endpoint out of range");
+}
+
+// explicitEdgeCheck(S, edge) (DRRT_Q.jl:1802-1826) of EVERY out-edge of a resident edge set: the two-stage kernels
+// over the set's prepared item records (no per-call gathers of node positions in the collect stage).
+void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radius, uint32_t flags, uint8_t *collide_out) {
+  rrtqx_tree *tree = E->tree;
+  rrtqx_ctx *ctx = tree->ctx;
+  cudaStream_t st = ctx->stream;
+  RQ_REQUIRE(tree->d == 3, "SimpleEdge checks need a 3-D tree (explicitEdgeCheck3D)");
+  RQ_REQUIRE(spheres->ctx == ctx, "obstacle set of another context");
+  if (E->dirty || tree->n != E->n_nodes) edges_rebuild(E);
+  const int64_t n = E->n_edges;
+  if (n <= 0) return;
+  RQ_REQUIRE(collide_out != nullptr, "collide_out is NULL");
+  const bool out_dev = is_device_ptr(collide_out);
+  uint8_t *dout = collide_out;
+  if (!out_dev) { ctx->stage_u8.ensure((size_t)n, st); dout = ctx->stage_u8.p; }
+  {
+    PhaseScope ph(ctx, "edges_check");
+    const int32_t *n_live = nullptr;
+    SphereTable tab = build_sphere_table(ctx, spheres, robot_radius, flags, &n_live);
+    SphereTableBufs &b = table_bufs(ctx);
+    b.rec2.ensure((size_t)spheres->n + 1, st);
+    b.thr2.ensure((size_t)spheres->n + 1, st);
+    b.frec2.ensure((size_t)spheres->n + 1, st);
+    b.cstart.ensure(SG_MAX_CELLS + 4, st);
+    b.grid.ensure(sizeof(SphGrid) + 16, st);
+    SphGrid *dG = (SphGrid *)b.grid.p;
+    const bool want_cover = spheres->n <= COV_MAX_OBSTACLES;
+    const int want_level = want_cover ? 2 : 1;
+    SphCoverBufs &cv = cover_bufs(ctx);
+    const bool cached = b.grid_level == want_level && (!want_cover || cv.build_id == b.cover_id);
+    if (!cached) {
+      sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, want_cover ? 1 : 0);
+      post_launch(ctx);
+      b.grid_level = want_level;
+      if (want_cover) {
+        build_sphere_cover(ctx, cv, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG, (int)spheres->n);
+        b.cover_id = cv.build_id;
+      }
+    }
+    ResidentEdgeSrc S{ItemRecords{E->item_frec.p, E->item_exact.p}, dout};
+    if (flags & RRTQX_CHECK_FMA_DOT) pq_launch<true>(ctx, cv, S, n, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
+    else                             pq_launch<false>(ctx, cv, S, n, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
+  }
+  if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n);
+  RQ_CUDA(cudaStreamSynchronize(st));
 }
 
 // explicitPointCheck (DRRT_Q.jl:1520-1556) / explicitPointCheck3D (:1558-1590),

@@ -44,6 +44,10 @@ struct rrtqx_edges {
   rrtqx::DevBuf<double> lmax;                 // per node: longest out/parent edge (cull bound)
   rrtqx::DevBuf<uint8_t> degenerate;          // per node: some edge has len == 0 or non-finite ends
   rrtqx::DevBuf<int32_t> scan_tmp;
+  // per-item records of the two-stage collision kernels (collide_queue.cuh: ItemRecords), items = out-edges in
+  // upload order, then one parent edge per node; rebuilt with the CSR
+  rrtqx::DevBuf<float4> item_frec;
+  rrtqx::DevBuf<double2> item_exact;
   // DubinsEdge trajectories (edge.trajectory[:,1:2]) of the ITEMS = out-edges in upload order, then one parent edge
   // per node: uploaded (traj_ptr / traj_xy) or solved on the device (`solved`); d_traj_* point at whichever is current
   rrtqx::DevBuf<int64_t> traj_ptr;
@@ -93,6 +97,8 @@ void edge_check_launch(rrtqx_ctx *ctx, const rrtqx_tree *tree, const rrtqx_spher
                        double robot_radius, uint32_t flags, uint8_t *collide_out, const int32_t **bad_dev);
 void node_check(rrtqx_ctx *ctx, const rrtqx_spheres *spheres, const double *points, int64_t n, double robot_radius,
                 uint32_t flags, uint8_t *collide_out, double *cert_out);
+// explicitEdgeCheck(S, edge) of every resident out-edge (collision.cu)
+void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radius, uint32_t flags, uint8_t *collide_out);
 // sweep.cu
 void edges_upload(rrtqx_edges *E, const int32_t *src, const int32_t *dst, int64_t ne, const int32_t *parent,
                   int64_t n_parent);

@@ -91,6 +91,13 @@ void edges_rebuild(rrtqx_edges *E) {
                                                     E->has_parent ? E->parent.p : nullptr, nn, E->lmax.p, E->degenerate.p);
     post_launch(ctx);
   }
+  if (t->d == 3 && ne + nn > 0) {  // per-item records of the two-stage sphere-world kernels: one pass over the node table
+    E->item_frec.ensure((size_t)(ne + nn) + 1, st);
+    E->item_exact.ensure(3 * (size_t)(ne + nn) + 3, st);
+    item_records_kernel<<<div_up(ne + nn, TB), TB, 0, st>>>(t->pos.p, nn, E->src.p, E->dst.p, ne,
+                                                            E->has_parent ? E->parent.p : nullptr, E->item_frec.p, E->item_exact.p);
+    post_launch(ctx);
+  }
   E->dirty = false;
 }
 
@@ -394,27 +401,21 @@ add_sweep_edge_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const in
 // per node; a colliding (edge, obstacle) pair counts only if the edge's start node passes the obstacle's
 // start-node filter.
 struct SweepEdgeSrc {
-  const double4 *pos;
+  static constexpr bool RESIDENT = true;   // item records built with the edge set (collide_queue.cuh: ItemRecords)
+  ItemRecords rec;
   int64_t n_edges;
-  const int32_t *src, *dst, *parent;
+  const int32_t *src;
   const double2 *ext;
   uint8_t *edge_flag, *node_flag;
+  __device__ __forceinline__ float4 frec(int64_t i) const { return rec.frec[i]; }
   __device__ __forceinline__ bool endpoints(int64_t i, double a[3], double b[3], int &v) const {
-    int w;
-    if (i >= n_edges) {
-      v = (int)(i - n_edges);
-      w = parent ? parent[v] : -1;
-      if (w < 0) return false;
-    } else {
-      v = src[i];
-      w = dst[i];
-    }
-    const double4 pa = pos[v], pb = pos[w];
-    a[0] = pa.x; a[1] = pa.y; a[2] = pa.z;
-    b[0] = pb.x; b[1] = pb.y; b[2] = pb.z;
+    const double2 p0 = rec.exact[3 * i], p1 = rec.exact[3 * i + 1], p2 = rec.exact[3 * i + 2];
+    a[0] = p0.x; a[1] = p0.y; a[2] = p1.x;
+    b[0] = p1.y; b[1] = p2.x; b[2] = p2.y;
+    v = i >= n_edges ? (int)(i - n_edges) : src[i];   // start node (the root is admitted with <= by accept())
     return true;
   }
-  __device__ __forceinline__ void clear(int64_t) const {}  // flags are zeroed by prepare_result
+  __device__ __forceinline__ void clear(int64_t) const {}  // flags are zeroed by sweep_prepare_result
   __device__ __forceinline__ bool accept(int o, const double4 &r, const double a[3], int v) const {
     const double q[3] = {r.x, r.y, r.z};
     const double s = sqdist<3>(q, a[0], a[1], a[2], 0.0);  // euclid(ob.position, startNode.position)
@@ -595,7 +596,7 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
       if (use_queue) {
         SphCoverBufs &cv = cover_bufs(ctx);
         if (n_obs <= COV_MAX_OBSTACLES) build_sphere_cover(ctx, cv, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG, (int)n_obs);
-        SweepEdgeSrc Q{E->tree->pos.p, E->n_edges, E->src.p, E->dst.p, par, R->ob_ext2.p, R->edge_flag.p, R->node_flag.p};
+        SweepEdgeSrc Q{ItemRecords{E->item_frec.p, E->item_exact.p}, E->n_edges, E->src.p, R->ob_ext2.p, R->edge_flag.p, R->node_flag.p};
         if (flags & RRTQX_CHECK_FMA_DOT) pq_launch<true>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
         else                             pq_launch<false>(ctx, cv, Q, work, R->ob_rec2.p, R->ob_thr2.p, R->ob_frec2.p, R->cstart.p, dG);
       } else if (flags & RRTQX_CHECK_FMA_DOT)

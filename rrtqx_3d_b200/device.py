@@ -384,6 +384,13 @@ class EdgeSet:
         node_ids, parent_ids = A.as_i32(node_ids), A.as_i32(parent_ids)
         A.check(self.L.rrtqx_edges_set_parents(self.h, A.ptr(node_ids), A.ptr(parent_ids), len(node_ids)), self.ctx.h)
 
+    def check_all(self, spheres: SphereSet, robot_radius, flags=0, out=None):
+        """explicitEdgeCheck(S, edge) of every resident out-edge -> uint8[n_edges] (edge id order)."""
+        if out is None:
+            out = np.empty(len(self), dtype=np.uint8)
+        A.check(self.L.rrtqx_edges_check_batch(self.h, spheres.h, float(robot_radius), int(flags), A.ptr(out)), self.ctx.h)
+        return out
+
     def add_sweep(self, spheres: SphereSet, ob_ids, robot_radius, delta, flags=0, result: SweepResult | None = None):
         ob_ids = A.as_i32(ob_ids)
         if result is None:

@@ -538,3 +538,56 @@ def test_handles_may_be_destroyed_in_any_order():
         S2 = SphereSet(c2, c, rad)
         assert edge_check_batch(t2, S2, src, dst, W.ROBOT_RADIUS).shape == (4000,)
         S2.close(); t2.close(); c2.close()
+
+
+def test_resident_edge_check_equals_batch_check_and_oracle(ctx):
+    """rrtqx_edges_check_batch (every resident out-edge, prepared per-item records: FP32 midpoint / half-length for the
+    collect stage, exact end points for the test stage) gives the flags of rrtqx_edge_check_batch and of the oracle;
+    zero-length edges, long edges, edges far outside the obstacle box, pathological obstacle sets, both dot forms,
+    and an edge set that grows and gets new parents in between."""
+    import os
+    pts, _, _ = W.c2_workload(12000, 1)
+    t, src, dst, parent = _neighbour_graph(ctx, pts, 1.6)
+    n0 = len(pts)
+    far = np.array([[900.0, 900.0, 900.0], [900.2, 900.1, 900.0], [-700.0, 3.0, 2.0], [-700.1, 3.1, 2.2]])
+    pts2 = np.ascontiguousarray(np.vstack([pts, far]))
+    t.insert_batch(far)
+    extra_s = np.array([n0, n0 + 1, n0 + 2, n0 + 3, 5, 17, 40, 41], dtype=np.int32)
+    extra_d = np.array([n0 + 1, n0, n0 + 3, n0 + 2, 5, 9000, 40, n0], dtype=np.int32)   # incl. zero-length and long edges
+    src2, dst2 = np.concatenate([src, extra_s]), np.concatenate([dst, extra_d])
+    rng = np.random.default_rng(8)
+    sets = {
+        "c3": W.c3_obstacles(256),
+        "huge": (rng.uniform(-20, 20, (3000, 3)), rng.uniform(10.0, 15.0, 3000)),        # cover over budget
+        "tiny": (rng.uniform(-20, 20, (2000, 3)), rng.uniform(0.01, 0.2, 2000)),
+        "mixed": (np.vstack([rng.uniform(-20, 20, (60, 3)), [[1e3, 1e3, 1e3]], [[np.nan, 0.0, 0.0]]]),
+                  np.concatenate([rng.uniform(0.5, 3.0, 60), [1.0], [1.0]])),
+    }
+    E = EdgeSet(t)
+    E.upload(src, dst, parent)
+    E.append(extra_s, extra_d)                       # the records follow the grown edge set
+    for name, (c, r) in sets.items():
+        c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
+        S = SphereSet(ctx, c, r)
+        sph, ns = oracle.make_spheres(c, r)
+        for fma in (0, 1):
+            fl = A.CHECK_FMA_DOT if fma else 0
+            got = E.check_all(S, W.ROBOT_RADIUS, flags=fl)
+            want = _orc_edges(sph, ns, pts2, src2, dst2, W.ROBOT_RADIUS, fma)
+            assert np.array_equal(got, want), (name, fma, int((got != want).sum()))
+            assert np.array_equal(got, edge_check_batch(t, S, src2, dst2, W.ROBOT_RADIUS, flags=fl)), (name, fma)
+        if name in ("c3", "tiny"):
+            assert 0 < got.sum() < len(got)
+    # the sweep over the same records: forced two-stage path == thread-per-edge path == (already oracle-checked) default
+    c, r = sets["c3"]
+    S = SphereSet(ctx, c, r)
+    ids = np.arange(64, dtype=np.int32)
+    ref = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()
+    os.environ["RRTQX_COVER_MIN_ITEMS"] = "1"
+    ctx.reload_tuning()
+    try:
+        forced = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()
+    finally:
+        del os.environ["RRTQX_COVER_MIN_ITEMS"]
+        ctx.reload_tuning()
+    assert np.array_equal(ref[0], forced[0]) and np.array_equal(ref[1], forced[1]) and len(ref[0]) > 0
