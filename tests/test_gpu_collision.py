@@ -564,7 +564,7 @@ def test_resident_edge_check_equals_batch_check_and_oracle(ctx):
                   np.concatenate([rng.uniform(0.5, 3.0, 60), [1.0], [1.0]])),
     }
     E = EdgeSet(t)
-    E.upload(src, dst, parent)
+    E.upload(src, dst, np.concatenate([parent, np.full(len(far), -1, dtype=np.int32)]))
     E.append(extra_s, extra_d)                       # the records follow the grown edge set
     for name, (c, r) in sets.items():
         c, r = np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
