@@ -221,8 +221,11 @@ edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ s
                   const double *__restrict__ starts, const double *__restrict__ ends, int64_t n_edges,
                   SphereTable tab, const int32_t *__restrict__ n_live, uint8_t *__restrict__ out, int n_nodes,
                   int32_t *__restrict__ bad) {
-  __shared__ double4 s_rec[SPH_TILE];
-  __shared__ double2 s_thr[SPH_TILE];
+  __shared__ alignas(128) double4 s_rec[SPH_TILE];
+  __shared__ alignas(128) double2 s_thr[SPH_TILE];
+  __shared__ alignas(8) unsigned long long s_bar;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  unsigned phase = 0;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_obs = *n_live;
   SegPre pre;
@@ -246,12 +249,8 @@ edge_check_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__ s
   bool hit = false;
   for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
     const int tn = min(SPH_TILE, n_obs - t0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
-      s_rec[k] = tab.rec[t0 + k];
-      s_thr[k] = tab.thr[t0 + k];
-    }
-    __syncthreads();
+    // obstacle tile -> shared memory by the TMA engine (regular tile: tn x 32 B + tn x 16 B, contiguous)
+    tma_stage_tile(s_rec, tab.rec + t0, (unsigned)tn * 32u, s_thr, tab.thr + t0, (unsigned)tn * 16u, &s_bar, phase);
     if (valid && !hit) {
       for (int k = 0; k < tn; ++k) {
         double4 o = s_rec[k];
@@ -422,7 +421,10 @@ template <bool QUICK>
 __global__ void __launch_bounds__(256)
 node_check_kernel(const double *__restrict__ pts, int64_t n, SphereTable tab, const int32_t *__restrict__ n_live,
                   double robot_radius, uint8_t *__restrict__ out, double *__restrict__ cert_out) {
-  __shared__ double4 s_rec[SPH_TILE];
+  __shared__ alignas(128) double4 s_rec[SPH_TILE];
+  __shared__ alignas(8) unsigned long long s_bar;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  unsigned phase = 0;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_obs = *n_live;
   const bool valid = i < n;
@@ -432,9 +434,7 @@ node_check_kernel(const double *__restrict__ pts, int64_t n, SphereTable tab, co
   if (QUICK) {  // quickCheck :1434-1452 -> quickCheck2D :1402-1415
     for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
       const int tn = min(SPH_TILE, n_obs - t0);
-      __syncthreads();
-      for (int k = threadIdx.x; k < tn; k += blockDim.x) s_rec[k] = tab.rec[t0 + k];
-      __syncthreads();
+      tma_stage_tile(s_rec, tab.rec + t0, (unsigned)tn * 32u, nullptr, nullptr, 0u, &s_bar, phase);
       if (valid && !hit)
         for (int k = 0; k < tn; ++k) {
           double4 o = s_rec[k];
@@ -447,9 +447,7 @@ node_check_kernel(const double *__restrict__ pts, int64_t n, SphereTable tab, co
   double ret_cert = INFINITY;
   for (int t0 = 0; t0 < n_obs; t0 += SPH_TILE) {
     const int tn = min(SPH_TILE, n_obs - t0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < tn; k += blockDim.x) s_rec[k] = tab.rec[t0 + k];
-    __syncthreads();
+    tma_stage_tile(s_rec, tab.rec + t0, (unsigned)tn * 32u, nullptr, nullptr, 0u, &s_bar, phase);
     if (valid && !hit)
       for (int k = 0; k < tn; ++k) {  // explicitPointCheck2D :1463-1487
         double4 o = s_rec[k];

@@ -315,6 +315,47 @@ __device__ __forceinline__ double jl_max(double x, double y) {
   return (y != y) ? y : x;
 }
 
+// ---- TMA (bulk asynchronous copy engine) staging of regular tiles: global -> shared, completion on an mbarrier.
+// One thread arms the barrier with the byte count and issues the copies; every thread of the block waits on the
+// barrier's phase.  No register round trip, no per-thread address arithmetic, and the LSU stays free while a tile is
+// in flight.  Addresses and sizes must be multiples of 16 bytes (cudaMalloc'ed tables of 16 / 32-byte records are).
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+// Stage `n` records of two parallel tables (recA: sizeA bytes each, recB optional) as one tile.  Called by ALL
+// threads of the block: a block barrier protects the previous tile's readers, thread 0 issues, everybody waits.
+__device__ __forceinline__ void tma_stage_tile(void *sA, const void *gA, unsigned bytesA, void *sB, const void *gB,
+                                               unsigned bytesB, unsigned long long *bar, unsigned &phase) {
+  __syncthreads();  // the previous tile is no longer read
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytesA + bytesB);
+    tma_load_1d(sA, gA, bytesA, bar);
+    if (bytesB) tma_load_1d(sB, gB, bytesB, bar);
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

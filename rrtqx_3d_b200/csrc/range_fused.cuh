@@ -533,6 +533,10 @@ static void range_query_fused(rrtqx_tree *t, const double *dq, const double *dr,
         // v5 (FP32 filter scan, packed exact records, 16-bit hit codes): hit buffers leave 32*V5_U entries of
         // head-room; the octet table must hold a whole pair's region (else the pair takes the exact routine)
         const int v5_nw = ctx->tune.v5_nw;
+#ifdef RRTQX_EXPERIMENT
+        if (variant == 0 && v5_nw == 32) RQ_V5(32, 704, 256);
+        else
+#endif
         if (variant == 0 && v5_nw == 28) RQ_V5(28, 704, 256);
         else if (variant == 0 && v5_nw == 20) RQ_V5(20, 704, 256);
         else if (variant == 0) RQ_V5(24, 704, 256);     // 24 warps/SM (80 registers), 94 KB shared

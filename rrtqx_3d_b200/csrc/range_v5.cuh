@@ -161,7 +161,10 @@ __device__ __noinline__ int v5_exact_query(const GridView *gp, const double *qpt
 template <int D, bool TAIL>
 __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, unsigned sbuf_k, unsigned stab, int n, int lane,
                                          int32_t *__restrict__ oi, double *__restrict__ od) {
-  constexpr int U = 4;
+#ifndef V5_FLUSH_U
+#define V5_FLUSH_U 4
+#endif
+  constexpr int U = V5_FLUSH_U;  // rows of 32 hits in flight per flush step
   auto fetch = [&](unsigned h, int &node, double4 &p) {
     if (!TAIL || !(h & 0x8000u)) {
       const int ent = lds32(stab + 4u * (h >> 3));
@@ -206,7 +209,7 @@ __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, uns
       }
   };
   const int rem = n - n_full;
-  if (rem > 64) tail(std::integral_constant<int, 4>{});
+  if (U >= 4 && rem > 64) tail(std::integral_constant<int, (U >= 4 ? 4 : 1)>{});
   else if (rem > 32) tail(std::integral_constant<int, 2>{});
   else if (rem > 0) tail(std::integral_constant<int, 1>{});
 }

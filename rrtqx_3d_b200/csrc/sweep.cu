@@ -247,9 +247,12 @@ add_sweep_kernel(const double4 *__restrict__ pos, int n_nodes, const int32_t *__
                  const uint8_t *__restrict__ degenerate, const double4 *__restrict__ ob_rec,
                  const double4 *__restrict__ ob_par, int n_obs, uint8_t *__restrict__ edge_flag,
                  uint8_t *__restrict__ node_flag, unsigned long long *__restrict__ stats) {
-  __shared__ double4 s_rec[SW_TILE];
-  __shared__ double4 s_par[SW_TILE];
+  __shared__ alignas(128) double4 s_rec[SW_TILE];
+  __shared__ alignas(128) double4 s_par[SW_TILE];
   __shared__ unsigned long long s_stats[2];
+  __shared__ alignas(8) unsigned long long s_bar;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  unsigned phase = 0;
   const int lane = lane_id();
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -258,9 +261,8 @@ add_sweep_kernel(const double4 *__restrict__ pos, int n_nodes, const int32_t *__
 
   for (int t0 = 0; t0 < n_obs; t0 += SW_TILE) {
     const int tn = min(SW_TILE, n_obs - t0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < tn; k += blockDim.x) { s_rec[k] = ob_rec[t0 + k]; s_par[k] = ob_par[t0 + k]; }
-    __syncthreads();
+    // obstacle tile (records + parameters, tn x 32 B each) -> shared memory by the TMA engine
+    tma_stage_tile(s_rec, ob_rec + t0, (unsigned)tn * 32u, s_par, ob_par + t0, (unsigned)tn * 32u, &s_bar, phase);
     for (int v = warp0; v < n_nodes; v += nwarps) {
       const double4 p = pos[v];
       const int ra = row_ptr[v], rb = row_ptr[v + 1];
@@ -436,10 +438,12 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
                     const double4 *__restrict__ ob_par, int n_tab, int removed_inactive,
                     uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag,
                     unsigned long long *__restrict__ stats) {
-  __shared__ double4 s_rec[SW_TILE];
-  __shared__ double4 s_par[SW_TILE];
+  __shared__ alignas(128) double4 s_rec[SW_TILE];
+  __shared__ alignas(128) double4 s_par[SW_TILE];
   __shared__ unsigned s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
+  __shared__ alignas(8) unsigned long long s_bar;
+  if (threadIdx.x == 0) { s_cnt = 0; mbar_init(&s_bar, 1); }
+  unsigned phase = 0;
   __syncthreads();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e < n_edges;
@@ -467,9 +471,7 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
   bool conflicts = false;
   for (int t0 = 1; t0 < n_tab; t0 += SW_TILE) {  // :3326-3337 every other active obstacle
     const int tn = min(SW_TILE, n_tab - t0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < tn; k += blockDim.x) { s_rec[k] = ob_rec[t0 + k]; s_par[k] = ob_par[t0 + k]; }
-    __syncthreads();
+    tma_stage_tile(s_rec, ob_rec + t0, (unsigned)tn * 32u, s_par, ob_par + t0, (unsigned)tn * 32u, &s_bar, phase);
     if (pending && !conflicts)
       for (int k = 0; k < tn; ++k)
         if (seg_sphere_collide<FMA_DOT>(pre, s_rec[k].x, s_rec[k].y, s_rec[k].z, s_par[k].x, s_par[k].y)) {
