@@ -192,6 +192,15 @@ struct BatchEdgeSrc {
   __device__ __forceinline__ void mark(int64_t i) const { out[i] = 1; }
 };
 
+// Sink of the obstacle-centric resident check (item_grid.cuh): explicitEdgeCheck(S, edge) has no extra condition;
+// parent-edge items of the grid are not part of the result.
+struct CheckGridSink {
+  int64_t n_edges;
+  uint8_t *out;
+  __device__ __forceinline__ bool accept(const IgObstacle &, const double *, int it) const { return it < n_edges; }
+  __device__ __forceinline__ void mark(int it) const { out[it] = 1; }
+};
+
 // Resident form: every out-edge of an rrtqx_edges set, item records prepared when the set was built.
 struct ResidentEdgeSrc {
   static constexpr bool RESIDENT = true;
@@ -396,9 +405,27 @@ void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radi
     SphGrid *dG = (SphGrid *)b.grid.p;
     const bool want_cover = spheres->n <= COV_MAX_OBSTACLES;
     const int want_level = want_cover ? 2 : 1;
+    bool grid_done = false;
+    if (E->igrid.valid && !ctx->tune.no_item_grid) {
+      // obstacle-centric: only the cells of the item grid an active obstacle can reach are read
+      RQ_CUDA(cudaMemsetAsync(dout, 0, (size_t)n, st));
+      CheckGridSink K{n, dout};
+      const int32_t *par = E->has_parent ? E->parent.p : nullptr;
+      const int32_t *ovf_dev;
+      if (flags & RRTQX_CHECK_FMA_DOT)
+        ovf_dev = item_grid_run<true>(ctx, E->igrid, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
+                                      E->n_nodes, E->src.p, E->dst.p, n, par);
+      else
+        ovf_dev = item_grid_run<false>(ctx, E->igrid, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
+                                       E->n_nodes, E->src.p, E->dst.p, n, par);
+      int32_t ovf = 0;
+      RQ_CUDA(cudaMemcpyAsync(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RQ_CUDA(cudaStreamSynchronize(st));
+      grid_done = ovf == 0;
+    }
     SphCoverBufs &cv = cover_bufs(ctx);
     const bool cached = b.grid_level == want_level && (!want_cover || cv.build_id == b.cover_id);
-    if (!cached) {
+    if (!grid_done && !cached) {
       sphere_grid_kernel<<<1, 1024, 0, st>>>(tab.rec, tab.thr, nullptr, n_live, 0, b.rec2.p, b.thr2.p, nullptr, b.cstart.p, dG, b.frec2.p, want_cover ? 1 : 0);
       post_launch(ctx);
       b.grid_level = want_level;
@@ -408,6 +435,8 @@ void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radi
       }
     }
     ResidentEdgeSrc S{ItemRecords{E->item_frec.p, E->item_exact.p}, dout};
+    if (grid_done) {
+    } else
     if (flags & RRTQX_CHECK_FMA_DOT) pq_launch<true>(ctx, cv, S, n, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
     else                             pq_launch<false>(ctx, cv, S, n, b.rec2.p, b.thr2.p, b.frec2.p, b.cstart.p, dG);
   }

@@ -108,7 +108,7 @@ inline bool is_device_ptr(const void *p) {
 namespace rrtqx {
 struct Tuning {
   bool edge_no_grid = false, edge_no_queue = false, dubins_check_v1 = false, range_two_pass = false,
-       nearest_warp = false;
+       nearest_warp = false, no_item_grid = false;
   int64_t cover_min_items = -1;  // < 0: the measured break-even defaults
   int fused_variant = -1;        // < 0: chosen from the expected neighbour count
   int range_kernel = 5, v5_nw = 24, qsort_s = 3, qsort_f = 1;
@@ -124,6 +124,7 @@ struct Tuning {
     dubins_check_v1 = on("RRTQX_DUBINS_CHECK_V1");
     range_two_pass = on("RRTQX_RANGE_TWO_PASS");
     nearest_warp = on("RRTQX_NEAREST_WARP");
+    no_item_grid = on("RRTQX_NO_ITEM_GRID");
     cover_min_items = geti("RRTQX_COVER_MIN_ITEMS", -1);
     fused_variant = (int)geti("RRTQX_FUSED_VARIANT", -1);
     range_kernel = (int)geti("RRTQX_RANGE_KERNEL", 5);

@@ -3,6 +3,7 @@
 #pragma once
 #include "collision.cuh"
 #include "common.cuh"
+#include "item_grid.cuh"
 #include "tree.cuh"
 
 struct rrtqx_range_result {
@@ -48,6 +49,8 @@ struct rrtqx_edges {
   // upload order, then one parent edge per node; rebuilt with the CSR
   rrtqx::DevBuf<float4> item_frec;
   rrtqx::DevBuf<double2> item_exact;
+  // the same items sorted by the grid cell of their midpoint: obstacle-centric sweeps / checks (item_grid.cuh)
+  rrtqx::ItemGridBufs igrid;
   // DubinsEdge trajectories (edge.trajectory[:,1:2]) of the ITEMS = out-edges in upload order, then one parent edge
   // per node: uploaded (traj_ptr / traj_xy) or solved on the device (`solved`); d_traj_* point at whichever is current
   rrtqx::DevBuf<int64_t> traj_ptr;

@@ -97,6 +97,10 @@ void edges_rebuild(rrtqx_edges *E) {
     item_records_kernel<<<div_up(ne + nn, TB), TB, 0, st>>>(t->pos.p, nn, E->src.p, E->dst.p, ne,
                                                             E->has_parent ? E->parent.p : nullptr, E->item_frec.p, E->item_exact.p);
     post_launch(ctx);
+    // and the items sorted by midpoint cell for the obstacle-centric kernels (item_grid.cuh)
+    item_grid_build(ctx, E->igrid, t->pos.p, nn, E->src.p, E->dst.p, ne, E->has_parent ? E->parent.p : nullptr);
+  } else {
+    E->igrid.valid = false;
   }
   E->dirty = false;
 }
@@ -429,6 +433,25 @@ struct SweepEdgeSrc {
   }
 };
 
+// Sink of the obstacle-centric add sweep (item_grid.cuh): a colliding (item, obstacle) pair counts only if the item's
+// START node passes the obstacle's start-node filter dist(c_o, v) < searchRange_o (root: <=), the reference's
+// candidate rule (findPointsInConflictWithObstacle, DRRT_Q.jl:3195-3204).
+struct SweepGridSink {
+  int64_t n_edges;
+  const int32_t *src;
+  uint8_t *edge_flag, *node_flag;
+  __device__ __forceinline__ bool accept(const IgObstacle &o, const double a[3], int it) const {
+    const double q[3] = {o.cx, o.cy, o.cz};
+    const double s = sqdist<3>(q, a[0], a[1], a[2], 0.0);  // euclid(ob.position, startNode.position)
+    if (s < o.ext_t) return true;
+    const int v = it >= n_edges ? (int)(it - n_edges) : src[it];
+    return v == 0 && __dsqrt_rn(s) <= o.ext_r;
+  }
+  __device__ __forceinline__ void mark(int it) const {
+    if (it >= n_edges) node_flag[it - n_edges] = 1; else edge_flag[it] = 1;
+  }
+};
+
 // removeObstacle: one thread per edge (upload order).  ob = table entry 0,
 // others = entries 1..n_tab-1 (thr / thr_le only).
 template <bool FMA_DOT>
@@ -581,7 +604,26 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
     R->ob_ext.ensure((size_t)n_obs, st);
     const int TB = 256;
     sweep_table_kernel<<<div_up(n_obs, TB), TB, 0, st>>>(S->rec.p, dids, (int)n_obs, robot_radius, delta, R->ob_rec.p, R->ob_par.p, R->ob_thr.p, R->ob_ext.p);
-    if (!(flags & RRTQX_SWEEP_STATS)) {
+    bool grid_done = false;
+    if (!(flags & RRTQX_SWEEP_STATS) && E->igrid.valid && !ctx->tune.no_item_grid) {
+      // obstacle-centric sweep over the items sorted by midpoint cell: only the cells an obstacle can reach are read
+      const int32_t *par = E->has_parent ? E->parent.p : nullptr;
+      SweepGridSink K{E->n_edges, E->src.p, R->edge_flag.p, R->node_flag.p};
+      const int32_t *ovf_dev;
+      if (flags & RRTQX_CHECK_FMA_DOT)
+        ovf_dev = item_grid_run<true>(ctx, E->igrid, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
+                                      E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par);
+      else
+        ovf_dev = item_grid_run<false>(ctx, E->igrid, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
+                                       E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par);
+      int32_t ovf = 0;
+      RQ_CUDA(cudaMemcpyAsync(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RQ_CUDA(cudaStreamSynchronize(st));
+      grid_done = ovf == 0;   // more work units than the list holds (huge obstacles): the edge-centric kernels take over
+      no_stats = true;
+    }
+    if (grid_done) {
+    } else if (!(flags & RRTQX_SWEEP_STATS)) {
       // edge-centric sweep over the obstacle grid (no candidate / pair statistics)
       R->ob_rec2.ensure((size_t)n_obs + 1, st);
       R->ob_thr2.ensure((size_t)n_obs + 1, st);

@@ -381,7 +381,11 @@ def test_two_stage_and_thread_per_edge_paths_agree(ctx):
     small = slice(0, 6000)                      # 4096 <= n < 16384: thread-per-edge grid kernel by default
     want = _orc_edges(sph, ns, pts, src, dst, W.ROBOT_RADIUS)
     results = {}
-    for mode, env in (("default", {}), ("no_queue", {"RRTQX_EDGE_NO_QUEUE": "1"}), ("forced", {"RRTQX_COVER_MIN_ITEMS": "1"})):
+    # the add sweep over a resident edge set takes the obstacle-centric item grid by default; RRTQX_NO_ITEM_GRID=1 gives
+    # the edge-centric kernels, whose own variants are then selected as before
+    for mode, env in (("default", {}), ("edge_centric", {"RRTQX_NO_ITEM_GRID": "1"}),
+                      ("no_queue", {"RRTQX_NO_ITEM_GRID": "1", "RRTQX_EDGE_NO_QUEUE": "1"}),
+                      ("forced", {"RRTQX_NO_ITEM_GRID": "1", "RRTQX_COVER_MIN_ITEMS": "1"})):
         for k, v in env.items():
             os.environ[k] = v
         ctx.reload_tuning()
@@ -582,12 +586,28 @@ def test_resident_edge_check_equals_batch_check_and_oracle(ctx):
     c, r = sets["c3"]
     S = SphereSet(ctx, c, r)
     ids = np.arange(64, dtype=np.int32)
-    ref = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()
-    os.environ["RRTQX_COVER_MIN_ITEMS"] = "1"
-    ctx.reload_tuning()
-    try:
-        forced = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()
-    finally:
-        del os.environ["RRTQX_COVER_MIN_ITEMS"]
+    ref = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()                  # obstacle-centric item grid
+    sph, ns = oracle.make_spheres(c[:64], r[:64])
+    for env in ({"RRTQX_NO_ITEM_GRID": "1"}, {"RRTQX_NO_ITEM_GRID": "1", "RRTQX_COVER_MIN_ITEMS": "1"}):
+        os.environ.update(env)
         ctx.reload_tuning()
-    assert np.array_equal(ref[0], forced[0]) and np.array_equal(ref[1], forced[1]) and len(ref[0]) > 0
+        try:
+            other = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA).fetch()
+            flags_ec = E.check_all(S, W.ROBOT_RADIUS)                              # edge-centric resident check
+        finally:
+            for k in env:
+                del os.environ[k]
+            ctx.reload_tuning()
+        assert np.array_equal(ref[0], other[0]) and np.array_equal(ref[1], other[1]) and len(ref[0]) > 0
+        assert np.array_equal(flags_ec, E.check_all(S, W.ROBOT_RADIUS))
+    # single obstacles (the planner's real call): a few cells of the grid instead of every item
+    for o in (0, 7, 63):
+        one = E.add_sweep(S, [o], W.ROBOT_RADIUS, W.DELTA).fetch()
+        os.environ["RRTQX_NO_ITEM_GRID"] = "1"
+        ctx.reload_tuning()
+        try:
+            want = E.add_sweep(S, [o], W.ROBOT_RADIUS, W.DELTA).fetch()
+        finally:
+            del os.environ["RRTQX_NO_ITEM_GRID"]
+            ctx.reload_tuning()
+        assert np.array_equal(one[0], want[0]) and np.array_equal(one[1], want[1])
