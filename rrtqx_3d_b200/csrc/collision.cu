@@ -197,7 +197,9 @@ struct BatchEdgeSrc {
 struct CheckGridSink {
   int64_t n_edges;
   uint8_t *out;
-  __device__ __forceinline__ bool accept(const IgObstacle &, const double *, int it) const { return it < n_edges; }
+  bool fast_ok;
+  __device__ __forceinline__ bool wants(int it) const { return it < n_edges; }
+  __device__ __forceinline__ bool accept(const IgObstacle &, const double *, int) const { return true; }
   __device__ __forceinline__ void mark(int it) const { out[it] = 1; }
 };
 
@@ -409,14 +411,14 @@ void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radi
     if (E->igrid.valid && !ctx->tune.no_item_grid) {
       // obstacle-centric: only the cells of the item grid an active obstacle can reach are read
       RQ_CUDA(cudaMemsetAsync(dout, 0, (size_t)n, st));
-      CheckGridSink K{n, dout};
+      CheckGridSink K{n, dout, true};
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
       const int32_t *ovf_dev;
       if (flags & RRTQX_CHECK_FMA_DOT)
-        ovf_dev = item_grid_run<true>(ctx, E->igrid, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
+        ovf_dev = item_grid_run<true>(ctx, E->igrid, &E->igrid1, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
                                       E->n_nodes, E->src.p, E->dst.p, n, par);
       else
-        ovf_dev = item_grid_run<false>(ctx, E->igrid, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
+        ovf_dev = item_grid_run<false>(ctx, E->igrid, &E->igrid1, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
                                        E->n_nodes, E->src.p, E->dst.p, n, par);
       int32_t ovf = 0;
       RQ_CUDA(cudaMemcpyAsync(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -50,7 +50,7 @@ struct rrtqx_edges {
   rrtqx::DevBuf<float4> item_frec;
   rrtqx::DevBuf<double2> item_exact;
   // the same items sorted by the grid cell of their midpoint: obstacle-centric sweeps / checks (item_grid.cuh)
-  rrtqx::ItemGridBufs igrid;
+  rrtqx::ItemGridBufs igrid, igrid1;   // level 0: all items; level 1: the items too long for level 0
   // DubinsEdge trajectories (edge.trajectory[:,1:2]) of the ITEMS = out-edges in upload order, then one parent edge
   // per node: uploaded (traj_ptr / traj_xy) or solved on the device (`solved`); d_traj_* point at whichever is current
   rrtqx::DevBuf<int64_t> traj_ptr;

@@ -98,7 +98,7 @@ void edges_rebuild(rrtqx_edges *E) {
                                                             E->has_parent ? E->parent.p : nullptr, E->item_frec.p, E->item_exact.p);
     post_launch(ctx);
     // and the items sorted by midpoint cell for the obstacle-centric kernels (item_grid.cuh)
-    item_grid_build(ctx, E->igrid, t->pos.p, nn, E->src.p, E->dst.p, ne, E->has_parent ? E->parent.p : nullptr);
+    item_grid_build_levels(ctx, E->igrid, E->igrid1, t->pos.p, nn, E->src.p, E->dst.p, ne, E->has_parent ? E->parent.p : nullptr);
   } else {
     E->igrid.valid = false;
   }
@@ -440,6 +440,8 @@ struct SweepGridSink {
   int64_t n_edges;
   const int32_t *src;
   uint8_t *edge_flag, *node_flag;
+  bool fast_ok;   // delta >= 0: a segment that lies within thr of the centre has its start node within searchRange
+  __device__ __forceinline__ bool wants(int) const { return true; }
   __device__ __forceinline__ bool accept(const IgObstacle &o, const double a[3], int it) const {
     const double q[3] = {o.cx, o.cy, o.cz};
     const double s = sqdist<3>(q, a[0], a[1], a[2], 0.0);  // euclid(ob.position, startNode.position)
@@ -511,17 +513,65 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
 }
 
 // ------------------------------------------------------- flag compaction
-// Ordered compaction of a byte-flag array into an id list without a per-element scan array: tile counts
-// (scan_tile_sums_kernel), a scan of the tile counts, then each block ranks its own tile of SCAN_TILE flags
-// (8 consecutive flags per thread) and writes the ids in ascending order.
+// Ordered compaction of the byte-flag arrays into id lists without a per-element scan array: tile counts, a scan of
+// the tile counts, then each block ranks its own tile of SCAN_TILE flags (8 consecutive flags per thread) and writes
+// the ids in ascending order.
+// Both flag arrays (edges, nodes) in one launch per stage: blocks [0, tiles_a) work on array A, the rest on array B.
 __global__ void __launch_bounds__(SCAN_THREADS)
-compact_tiles_kernel(const uint8_t *__restrict__ flag, int64_t n, const int32_t *__restrict__ tile_offsets,
-                     int32_t *__restrict__ out) {
+flag_tile_sums2_kernel(const uint8_t *__restrict__ fa, int64_t na, int tiles_a, int32_t *__restrict__ sums_a,
+                       const uint8_t *__restrict__ fb, int64_t nb, int32_t *__restrict__ sums_b) {
   __shared__ int32_t sm[33];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  const bool second = (int)blockIdx.x >= tiles_a;
+  const uint8_t *flag = second ? fb : fa;
+  const int64_t n = second ? nb : na;
+  const int tile = second ? blockIdx.x - tiles_a : blockIdx.x;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t cnt = 0;
+  if (base + SCAN_ITEMS <= n) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(flag + base);
+    cnt = __popc(__vcmpne4(w.x, 0u) & 0x01010101u) + __popc(__vcmpne4(w.y, 0u) & 0x01010101u);
+  } else {
+    for (int k = 0; k < SCAN_ITEMS; ++k) cnt += (base + k < n && flag[base + k]) ? 1 : 0;
+  }
+  int32_t tot;
+  block_exclusive_scan<int32_t>(cnt, sm, &tot);
+  if (threadIdx.x == 0) (second ? sums_b : sums_a)[tile] = tot;
+}
+__global__ void __launch_bounds__(1024) flag_scan_sums2_kernel(int32_t *__restrict__ sums_a, int64_t tiles_a,
+                                                               int32_t *__restrict__ sums_b, int64_t tiles_b) {
+  __shared__ int32_t sm[33];
+  __shared__ int32_t carry_s;
+  int32_t *tile_sums = blockIdx.x ? sums_b : sums_a;
+  const int64_t n_tiles = blockIdx.x ? tiles_b : tiles_a;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = (i < n_tiles) ? tile_sums[i] : 0;
+    int32_t tot;
+    const int32_t ex = block_exclusive_scan<int32_t>(v, sm, &tot);
+    const int32_t carry = carry_s;
+    if (i < n_tiles) tile_sums[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[n_tiles] = carry_s;  // grand total
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+flag_compact2_kernel(const uint8_t *__restrict__ fa, int64_t na, int tiles_a, const int32_t *__restrict__ off_a,
+                     int32_t *__restrict__ out_a, const uint8_t *__restrict__ fb, int64_t nb,
+                     const int32_t *__restrict__ off_b, int32_t *__restrict__ out_b) {
+  __shared__ int32_t sm[33];
+  const bool second = (int)blockIdx.x >= tiles_a;
+  const uint8_t *flag = second ? fb : fa;
+  const int64_t n = second ? nb : na;
+  const int tile = second ? blockIdx.x - tiles_a : blockIdx.x;
+  int32_t *out = second ? out_b : out_a;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   unsigned char f[SCAN_ITEMS];
   int32_t cnt = 0;
-  if (base + SCAN_ITEMS <= n) {  // flag arrays come from cudaMalloc and base is a multiple of 8
+  if (base + SCAN_ITEMS <= n) {
     const uint2 w = *reinterpret_cast<const uint2 *>(flag + base);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { f[k] = (w.x >> (8 * k)) & 0xff; f[4 + k] = (w.y >> (8 * k)) & 0xff; }
@@ -531,27 +581,33 @@ compact_tiles_kernel(const uint8_t *__restrict__ flag, int64_t n, const int32_t 
   }
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) cnt += f[k] ? 1 : 0;
-  int32_t pos = block_exclusive_scan<int32_t>(cnt, sm, (int32_t *)nullptr) + tile_offsets[blockIdx.x];
+  int32_t pos = block_exclusive_scan<int32_t>(cnt, sm, (int32_t *)nullptr) + (second ? off_b : off_a)[tile];
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k)
     if (f[k]) out[pos++] = (int32_t)(base + k);
 }
 
+// Flags -> ascending id lists.  The lists are allocated for the worst case (every edge / node), so the three stages run
+// back to back without a host round trip in the middle; the counts are read once, at the end.
 void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   cudaStream_t st = ctx->stream;
-  static_assert(SCAN_ITEMS == 8, "compact_tiles_kernel reads 8 flags per thread as one 64-bit word");
+  static_assert(SCAN_ITEMS == 8, "the flag kernels read 8 flags per thread as one 64-bit word");
   const int64_t et = (R->n_edges + SCAN_TILE - 1) / SCAN_TILE, nt = (R->n_nodes + SCAN_TILE - 1) / SCAN_TILE;
   R->edge_scan.ensure((size_t)et + 2, st);  // tile offsets, [et] = total
   R->node_scan.ensure((size_t)nt + 2, st);
-  RQ_CUDA(cudaMemsetAsync(R->edge_scan.p, 0, sizeof(int32_t), st));  // totals of empty arrays
-  RQ_CUDA(cudaMemsetAsync(R->node_scan.p, 0, sizeof(int32_t), st));
-  if (et) {
-    scan_tile_sums_kernel<uint8_t, int32_t><<<(unsigned)et, SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, R->edge_scan.p);
-    scan_sums_kernel<int32_t><<<1, 1024, 0, st>>>(R->edge_scan.p, et);
-  }
-  if (nt) {
-    scan_tile_sums_kernel<uint8_t, int32_t><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(R->node_flag.p, R->n_nodes, R->node_scan.p);
-    scan_sums_kernel<int32_t><<<1, 1024, 0, st>>>(R->node_scan.p, nt);
+  R->edge_list.ensure((size_t)R->n_edges + 1, st);
+  R->node_list.ensure((size_t)R->n_nodes + 1, st);
+  if (et + nt > 0) {
+    flag_tile_sums2_kernel<<<(unsigned)(et + nt), SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_scan.p,
+                                                                        R->node_flag.p, R->n_nodes, R->node_scan.p);
+    flag_scan_sums2_kernel<<<2, 1024, 0, st>>>(R->edge_scan.p, et, R->node_scan.p, nt);
+    flag_compact2_kernel<<<(unsigned)(et + nt), SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_scan.p,
+                                                                      R->edge_list.p, R->node_flag.p, R->n_nodes,
+                                                                      R->node_scan.p, R->node_list.p);
+    post_launch(ctx, 3);
+  } else {
+    RQ_CUDA(cudaMemsetAsync(R->edge_scan.p, 0, sizeof(int32_t), st));
+    RQ_CUDA(cudaMemsetAsync(R->node_scan.p, 0, sizeof(int32_t), st));
   }
   int32_t ne_hits = 0, nn_hits = 0;
   unsigned long long stats[2] = {0, 0};
@@ -563,11 +619,6 @@ void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
   R->n_node_hits = nn_hits;
   R->n_candidates = (int64_t)stats[0];
   R->n_pair_tests = (int64_t)stats[1];
-  R->edge_list.ensure((size_t)ne_hits + 1, st);
-  R->node_list.ensure((size_t)nn_hits + 1, st);
-  if (et) compact_tiles_kernel<<<(unsigned)et, SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, R->edge_scan.p, R->edge_list.p);
-  if (nt) compact_tiles_kernel<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(R->node_flag.p, R->n_nodes, R->node_scan.p, R->node_list.p);
-  post_launch(ctx, 6);
 }
 
 void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
@@ -608,19 +659,23 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
     if (!(flags & RRTQX_SWEEP_STATS) && E->igrid.valid && !ctx->tune.no_item_grid) {
       // obstacle-centric sweep over the items sorted by midpoint cell: only the cells an obstacle can reach are read
       const int32_t *par = E->has_parent ? E->parent.p : nullptr;
-      SweepGridSink K{E->n_edges, E->src.p, R->edge_flag.p, R->node_flag.p};
+      SweepGridSink K{E->n_edges, E->src.p, R->edge_flag.p, R->node_flag.p, delta >= 0.0};
       const int32_t *ovf_dev;
       if (flags & RRTQX_CHECK_FMA_DOT)
-        ovf_dev = item_grid_run<true>(ctx, E->igrid, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
+        ovf_dev = item_grid_run<true>(ctx, E->igrid, &E->igrid1, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
                                       E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par);
       else
-        ovf_dev = item_grid_run<false>(ctx, E->igrid, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
+        ovf_dev = item_grid_run<false>(ctx, E->igrid, &E->igrid1, R->ob_rec.p, R->ob_thr.p, R->ob_ext.p, nullptr, (int)n_obs, K,
                                        E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par);
+      // the overflow flag (more work units than the list holds: huge obstacles) is read together with the counts;
+      // on overflow nothing was marked and the edge-centric kernels repeat the sweep (below)
+      sweep_finish(ctx, R);
       int32_t ovf = 0;
-      RQ_CUDA(cudaMemcpyAsync(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      RQ_CUDA(cudaStreamSynchronize(st));
-      grid_done = ovf == 0;   // more work units than the list holds (huge obstacles): the edge-centric kernels take over
+      RQ_CUDA(cudaMemcpy(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost));
+      grid_done = ovf == 0;
       no_stats = true;
+      if (grid_done) { R->n_candidates = -1; R->n_pair_tests = -1; return; }
+      sweep_prepare_result(E, R);
     }
     if (grid_done) {
     } else if (!(flags & RRTQX_SWEEP_STATS)) {
