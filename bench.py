@@ -708,6 +708,12 @@ def main():
                     times.append(ctx.last_phase_ms("add_sweep"))
             assert sres.sizes()[:2] == (n_eh, n_nh)
             sms = float(np.mean(times))
+            # the planner's real call: ONE new obstacle (addNewObstacle, DRRT_Q.jl:3220) against the same resident graph
+            one_ms, one_hits = [], 0
+            for k in range(16):
+                E.add_sweep(S, ids[k:k + 1], W.ROBOT_RADIUS, W.DELTA, result=sres)
+                one_ms.append(ctx.last_phase_ms("add_sweep"))
+                one_hits += sres.sizes()[0]
             n_e = len(src)
             sbytes = args.nodes * 24 + n_e * 8 + args.sweep_obstacles * 40 + n_e * 1 + (n_eh + n_nh) * 4
             # C5-style batch: explicitEdgeCheck(S, edge) of every edge against all 256 active spheres
@@ -780,6 +786,7 @@ def main():
                                   "fp64_frac_of_unfused_peak_statistics_kernel": ops / (float(np.mean(times_stats)) / 1e3) / (fp64_tflops / 2 * 1e12),
                                   "edges": n_e, "obstacles": args.sweep_obstacles, "pair_checks": n_tests,
                                   "candidate_nodes": n_cand, "blocked_edges": n_eh, "orphans": n_nh, "ms": sms,
+                                  "single_obstacle_ms": float(np.median(one_ms)), "single_obstacle_mean_blocked_edges": one_hits / 16,
                                   "ms_with_statistics_kernel": float(np.mean(times_stats)),
                                   "edges_per_s": n_e / (sms / 1e3), "pair_checks_per_s": n_tests / (sms / 1e3),
                                   "algorithmic_bytes": sbytes, "hbm_frac": sbytes / (sms / 1e3) / 1e9 / peak_gbs}
