@@ -45,7 +45,8 @@ def measured_peaks():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (profiles/range_traffic.json, written by hand from the `ncu --set full` report of the C2 run)."""
+    (profiles/range_traffic.json, written by scripts/write_traffic.py from the same `ncu --set full` report as the
+    committed profile summary)."""
     p = os.path.join(ROOT, "profiles", "range_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -818,11 +819,30 @@ def main():
                 if it >= 3:
                     evs.append(a.elapsed_time(b))
             ems = float(np.mean(evs))
+            # weak-scaled form of the same check: EVERY rank holds the 9.85M-edge graph resident and checks all of it
+            # (world x 9.85M edges per step, rrtqx_edges_check_batch); the fixed-size result that is exchanged is each
+            # rank's count of colliding edges
+            E5 = EdgeSet(tree)
+            E5.upload(src, dst, None)
+            wflag = torch.empty(len(src), dtype=torch.uint8, device="cuda")
+            wevs = []
+            for it in range(3 + args.steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                E5.check_all(S5, W.ROBOT_RADIUS, out=wflag.data_ptr())
+                b.record(stream)
+                b.synchronize()
+                if it >= 3:
+                    wevs.append(a.elapsed_time(b))
+            wms = float(np.mean(wevs))
+            wcount = int(wflag.sum().item())
+            E5.close()
             done, secs = c5_instances(ctx, rank, world, args.c5_instances, args.c5_iterations)
             if world > 1:
-                tt = torch.tensor([ems, secs], device="cuda", dtype=torch.float64)
+                tt = torch.tensor([ems, secs, wms], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                ems, secs = float(tt[0].item()), float(tt[1].item())
+                ems, secs, wms = float(tt[0].item()), float(tt[1].item()), float(tt[2].item())
                 dd = torch.tensor([done], device="cuda", dtype=torch.int64)
                 dist.all_reduce(dd)
                 done = int(dd.item())
@@ -836,6 +856,9 @@ def main():
                                       "independent C1-style planning instances round-robin",
                           "comm": c5_info,
                           "edges": len(src), "edge_shards": world, "edge_batch_ms": ems,
+                          "edge_weak_ms": wms, "edge_weak_edges_per_s": world * len(src) / (wms / 1e3),
+                          "edge_weak_colliding_edges_rank0": wcount,
+                          "edge_weak_note": "every rank checks its own resident copy of the graph (world x edges per step)",
                           "edges_per_s": len(src) / (ems / 1e3), "colliding_edges": colliding, "scaling": "strong",
                           "instances": args.c5_instances, "iterations_per_instance": args.c5_iterations,
                           "instance_seconds": secs, "planner_iterations_per_s": done / secs}
