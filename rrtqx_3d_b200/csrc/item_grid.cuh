@@ -128,35 +128,44 @@ ig_bbox_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *
                unsigned long long *__restrict__ box /* min xyz, max xyz as ordered integers */,
                double *__restrict__ len_stats /* [0] sum of lengths, [1] count (cell-size heuristic only) */,
                const int32_t *__restrict__ ids /* NULL: items 0 .. n_edges + n_nodes */, int64_t n_ids) {
-  const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid-stride: every thread folds its items, one set of atomics per BLOCK (same-address atomics serialise)
+  __shared__ double s_red[8][8];
   const int64_t n_all = ids ? n_ids : n_edges + n_nodes;
-  const int64_t i = kk < n_all ? (ids ? (int64_t)ids[kk] : kk) : n_edges + n_nodes;   // past the end: no item
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   double len = 0.0, cntv = 0.0;
-  double4 a, b;
-  if (i < n_edges + n_nodes && ig_endpoints(pos, n_nodes, src, dst, n_edges, parent, i, a, b)) {
-    const IgItem t = ig_item(a, b);
-    if (!t.degenerate) { mn[0] = mx[0] = t.mx; mn[1] = mx[1] = t.my; mn[2] = mx[2] = t.mz; len = sqrt(t.s2); cntv = 1.0; }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    len += __shfl_xor_sync(FULL, len, o);
-    cntv += __shfl_xor_sync(FULL, cntv, o);
-  }
-  if ((threadIdx.x & 31) == 0 && cntv > 0.0) { atomicAdd(&len_stats[0], len); atomicAdd(&len_stats[1], cntv); }
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[c] = fmin(mn[c], __shfl_xor_sync(FULL, mn[c], o));
-      mx[c] = fmax(mx[c], __shfl_xor_sync(FULL, mx[c], o));
-    }
-  if ((threadIdx.x & 31) == 0)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (mn[c] <= mx[c]) {
-        atomicMin(&box[c], ig_ord(mn[c]));
-        atomicMax(&box[3 + c], ig_ord(mx[c]));
+  for (int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; kk < n_all; kk += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = ids ? (int64_t)ids[kk] : kk;
+    double4 a, b;
+    if (ig_endpoints(pos, n_nodes, src, dst, n_edges, parent, i, a, b)) {
+      const IgItem t = ig_item(a, b);
+      if (!t.degenerate) {
+        mn[0] = fmin(mn[0], t.mx); mx[0] = fmax(mx[0], t.mx);
+        mn[1] = fmin(mn[1], t.my); mx[1] = fmax(mx[1], t.my);
+        mn[2] = fmin(mn[2], t.mz); mx[2] = fmax(mx[2], t.mz);
+        len += sqrt(t.s2);
+        cntv += 1.0;
       }
     }
+  }
+  double v[8] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], len, cntv};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(FULL, v[k], o);
+      v[k] = k < 3 ? fmin(v[k], w) : (k < 6 ? fmax(v[k], w) : v[k] + w);
+    }
+    if (lane == 0) s_red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    double r = s_red[k][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = k < 3 ? fmin(r, s_red[k][w]) : (k < 6 ? fmax(r, s_red[k][w]) : r + s_red[k][w]);
+    if (k < 3) { if (r < INFINITY) atomicMin(&box[k], ig_ord(r)); }
+    else if (k < 6) { if (r > -INFINITY) atomicMax(&box[k], ig_ord(r)); }
+    else if (r > 0.0) atomicAdd(&len_stats[k - 6], r);
+  }
 }
 
 __device__ __forceinline__ int ig_cell(double v, double lo, double inv, int n) {
@@ -503,7 +512,8 @@ static inline void item_grid_build(rrtqx_ctx *ctx, ItemGridBufs &B, const double
   B.bbox.ensure(8, st);
   unsigned long long init[8] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull, 0ull, 0ull};  // box, then two doubles (0.0)
   RQ_CUDA(cudaMemcpyAsync(B.bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  ig_bbox_kernel<<<blocks, TB, 0, st>>>(pos, n_nodes, src, dst, n_edges, parent, (unsigned long long *)B.bbox.p, B.bbox.p + 6, ids, n_ids);
+  ig_bbox_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * 8), TB, 0, st>>>(
+      pos, n_nodes, src, dst, n_edges, parent, (unsigned long long *)B.bbox.p, B.bbox.p + 6, ids, n_ids);
   post_launch(ctx);
   unsigned long long box[8];
   RQ_CUDA(cudaMemcpyAsync(box, B.bbox.p, sizeof(box), cudaMemcpyDeviceToHost, st));
