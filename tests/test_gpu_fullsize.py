@@ -121,6 +121,53 @@ def test_c3_full_size_sweep_is_union_of_single_obstacle_sweeps(ctx, c2):
                                       oracle._p(np.ascontiguousarray(dst[sample]), oracle.c_i32p), 0, len(sample),
                                       W.ROBOT_RADIUS, 0, oracle._p(want, oracle.c_u8p), 8)
     assert np.array_equal(flags[sample], want)
+    # the whole sweep against the oracle's addNewObstacle loop (start-node filter, out-edge and parent-edge tests,
+    # orphan rule): every obstacle swept on the CPU over the SAME 10^6-node tree and 9.85 M-edge graph, a few
+    # obstacles per host thread; blocked-edge set, orphan set and both statistics must equal the GPU's
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    orc = oracle.KDTree(3)
+    orc.insert_batch(pts)
+    order = np.argsort(src, kind="stable")
+    row_ptr = np.zeros(len(pts) + 1, dtype=np.int64)
+    np.add.at(row_ptr, src + 1, 1)
+    row_ptr = np.cumsum(row_ptr)
+    col = np.ascontiguousarray(dst[order])
+    eid = order.astype(np.int32)
+    par = np.ascontiguousarray(parent, dtype=np.int32)
+    L = oracle.lib()
+    cap = len(src) + 8
+
+    def sweep_some(obs):
+        be = np.zeros(cap, dtype=np.int32)
+        on = np.zeros(len(pts) + 8, dtype=np.int32)
+        eflag = np.zeros(len(src), dtype=np.uint8)
+        nflag = np.zeros(len(pts), dtype=np.uint8)
+        nc_sum = nt_sum = 0
+        for o in obs:
+            nb, no, nc, nt = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            rc = L.orc_obstacle_add_sweep(orc.h, C.byref(sph[o]), W.ROBOT_RADIUS, W.DELTA, oracle._p(row_ptr, oracle.c_i64p),
+                                          oracle._p(col, oracle.c_i32p), oracle._p(par, oracle.c_i32p), 0,
+                                          oracle._p(be, oracle.c_i32p), C.byref(nb), cap, oracle._p(on, oracle.c_i32p),
+                                          C.byref(no), len(on), C.byref(nc), C.byref(nt))
+            assert rc == 0
+            eflag[eid[be[:nb.value]]] = 1
+            nflag[on[:no.value]] = 1
+            nc_sum += nc.value
+            nt_sum += nt.value
+        return eflag, nflag, nc_sum, nt_sum
+
+    workers = 16
+    with ThreadPoolExecutor(workers) as pool:
+        parts = list(pool.map(sweep_some, [range(k, 256, workers) for k in range(workers)]))
+    eflag = np.zeros(len(src), dtype=np.uint8)
+    nflag = np.zeros(len(pts), dtype=np.uint8)
+    for pe, pn, _, _ in parts:
+        eflag |= pe
+        nflag |= pn
+    assert np.array_equal(np.flatnonzero(eflag), np.sort(fe))
+    assert np.array_equal(np.flatnonzero(nflag), np.sort(fn))
+    assert (sum(p[2] for p in parts), sum(p[3] for p in parts)) == (n_cand, n_tests)
 
 
 def test_c4_full_size_wrap_queries_and_dubins(ctx):
