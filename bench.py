@@ -357,6 +357,49 @@ def c4_dubins(ctx, n_edges, steps):
         if it >= 3:
             kd_ms.append(ctx.last_phase_ms("range_query"))
     kd_ms = float(np.mean(kd_ms))
+    # the Otte / Dubins replanning sweep (DRRT.jl:3127-3197) on the C4 graph: every node's neighbours within 1.06 as
+    # out-edges, the first neighbour as parent, trajectories of all items solved on the device and kept resident
+    from rrtqx_3d_b200.device import EdgeSet, SweepResult
+    resn, totn = t4.range_query(nodes4, 1.06, want_dist=False)
+    cntn, offn = resn.layout()
+    idxn, _ = resn.fetch(want_dist=False)
+    by_off = np.argsort(offn, kind="stable")
+    srcn = np.repeat(by_off.astype(np.int32), cntn[by_off])
+    dstn = idxn[:totn].astype(np.int32)
+    keep = srcn != dstn
+    srcn, dstn = srcn[keep], dstn[keep]
+    o2 = np.argsort(srcn, kind="stable")
+    srcn, dstn = np.ascontiguousarray(srcn[o2]), np.ascontiguousarray(dstn[o2])
+    par = np.full(len(nodes4), -1, dtype=np.int32)
+    first = np.r_[True, srcn[1:] != srcn[:-1]]
+    par[srcn[first]] = dstn[first]
+    par[0] = -1
+    resn.close()
+    E4 = EdgeSet(t4)
+    E4.upload(srcn, dstn, par)
+    ctx.sync()
+    t0 = time.perf_counter()
+    rows4 = E4.solve_trajectories(1.0)
+    ctx.sync()
+    solve_all_ms = 1e3 * (time.perf_counter() - t0)
+    all_obs = np.arange(len(P.kind), dtype=np.int32)
+    sw = SweepResult(ctx)
+    sw_ms, one_ms = [], []
+    for it in range(3 + steps):
+        E4.add_sweep_2d(P, all_obs, 0.5, 5.0, 1.0, result=sw)
+        if it >= 3:
+            sw_ms.append(ctx.last_phase_ms("add_sweep_2d"))
+    blocked4, orphans4 = sw.sizes()[0], sw.sizes()[1]
+    for o in range(0, len(all_obs), max(1, len(all_obs) // 8)):
+        E4.add_sweep_2d(P, [o], 0.5, 5.0, 1.0, result=sw)
+        one_ms.append(ctx.last_phase_ms("add_sweep_2d"))
+    sweep_2d = {"nodes": len(nodes4), "edges": int(len(srcn)), "trajectory_rows": int(rows4), "obstacles": int(len(all_obs)),
+                "solve_trajectories_ms_wall": solve_all_ms, "ms": float(np.mean(sw_ms)),
+                "edges_per_s": len(srcn) / (float(np.mean(sw_ms)) / 1e3), "blocked_edges": int(blocked4),
+                "orphans": int(orphans4), "single_obstacle_ms": float(np.mean(one_ms)),
+                "note": "addNewObstacle of the Otte generation with DubinsEdge: theta-wrapped start-node filter, "
+                        "sampled-trajectory check of every out-edge and parent edge of the candidates"}
+    sw.close()
     # CPU sample
     L = oracle.lib()
     f = lambda a: oracle._p(np.ascontiguousarray(a, dtype=np.float64), oracle.c_f64p)
@@ -386,6 +429,7 @@ def c4_dubins(ctx, n_edges, steps):
             "cpu_edges_per_s": n_cpu / cpu_s, "cpu": f"oracle solver + check, 1 thread, first {n_cpu} edges "
                                                     "(python call overhead included)",
             "algorithmic_bytes": n_edges * (64 + 16 + 1) + rows * 16 * 2,
+            "sweep_2d": sweep_2d,
             "kd_wrap_queries": {"nodes": 200_000, "queries": 200_000, "radius": 1.06, "mean_neighbours": k4 / 200_000,
                                 "ms": kd_ms, "queries_per_s": 200_000 / (kd_ms / 1e3),
                                 "note": "theta ghost identities run as (real, ghost) pairs of the range kernel"}}

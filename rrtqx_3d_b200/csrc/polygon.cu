@@ -68,7 +68,10 @@ struct AllObstacles {
   __device__ __forceinline__ bool admit(int) const { return true; }
 };
 
-__global__ void __launch_bounds__(256)
+#ifndef DUBINS_MINB
+#define DUBINS_MINB 6  // FP64 dependency chains: latency-bound, 48 warps per SM beat 16 although 40 registers spill (0.93 -> 0.60 ms on C4)
+#endif
+__global__ void __launch_bounds__(256, DUBINS_MINB)
 dubins_check_kernel(PolyView P, int ignore_active, const double *__restrict__ starts, const double *__restrict__ ends,
                     const int64_t *__restrict__ tptr, const double *__restrict__ traj, int64_t n_edges, double rho,
                     double rho_coarse, uint8_t *__restrict__ out) {

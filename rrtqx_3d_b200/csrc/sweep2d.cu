@@ -83,9 +83,12 @@ struct ListedObstacles {  // the obstacles of the call, each with the start-node
   __device__ __forceinline__ bool admit(int k) const { return !filt || sweep2d_candidate<D>(filt[k], pv, v); }
 };
 
+#ifndef SWEEP2D_MINB
+#define SWEEP2D_MINB 6  // as DUBINS_MINB (polygon.cu): latency-bound FP64 chains, 48 warps per SM (16.7 -> 10.5 ms on the C4 graph)
+#endif
 // addNewObstacle: item i < n_edges is out-edge i (src[i] -> dst[i]); item n_edges + v is the parent edge of node v.
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SWEEP2D_MINB)
 add_sweep_2d_kernel(PolyView P, const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src,
                     const int32_t *__restrict__ dst, int64_t n_edges, const int32_t *__restrict__ parent,
                     const int64_t *__restrict__ tptr, const double *__restrict__ traj, const int32_t *__restrict__ ids,
@@ -114,7 +117,7 @@ add_sweep_2d_kernel(PolyView P, const double4 *__restrict__ pos, int64_t n_nodes
 
 // removeObstacle: ids[0] = the removed obstacle (still active while tested, :3228 vs :3267), ids[1..] = the others.
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SWEEP2D_MINB)
 remove_sweep_2d_kernel(PolyView P, const double4 *__restrict__ pos, const int32_t *__restrict__ src,
                        const int32_t *__restrict__ dst, int64_t n_edges, const uint8_t *__restrict__ edge_dist_inf,
                        const int64_t *__restrict__ tptr, const double *__restrict__ traj, const int32_t *__restrict__ ids,

@@ -1,14 +1,10 @@
 #!/bin/bash
-# parity + A/B of the Dubins trajectory check kernels (RRTQX_DUBINS_CHECK_V1=1: first form)
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dubins.py tests/test_gpu_collision.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
-CMD="python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-c1 --no-c5 --no-sweep"
-for mode in v2 v1; do
-  if [ $mode = v1 ]; then export RRTQX_DUBINS_CHECK_V1=1; else unset RRTQX_DUBINS_CHECK_V1; fi
-  timeout 600 $CMD > gpurun_out/dub_$mode.json 2> gpurun_out/dub_$mode.err || tail -5 gpurun_out/dub_$mode.err
-  python - <<PY
-import json
-l = json.loads(open("gpurun_out/dub_$mode.json").read().strip().splitlines()[-1])
-print("$mode", json.dumps(l.get("c4_dubins"))[:900])
-PY
+# A/B of builds of the Dubins trajectory check and the Otte / Dubins sweep: for each library name run the C4 leg only
+for lib in "$@"; do
+  RRTQX_B200_LIB=$PWD/rrtqx_3d_b200/$lib python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-sweep --no-c1 --no-c5 2>gpurun_out/exp_dubins.err | python -c '
+import json, sys
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])["dubins"]
+print(sys.argv[1], "check_ms %.4f" % d["check_ms"], "solve_ms %.4f" % d["solve_ms"], d["colliding_edges"],
+      {k: v for k, v in d.get("sweep_2d", {}).items() if k != "note"}, d.get("error"))
+' $lib
 done
