@@ -502,7 +502,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream()
+    # ONE stream for torch and the library.  torch's default stream has handle 0, which rrtqx_ctx_create reads as "no
+    # stream given" (it then creates its own): the flush memsets and the timing events would sit on another stream
+    # than the kernels they are meant to bracket.  A non-default torch stream has a real handle.
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ctx = Context(local_rank, stream.cuda_stream)
     comm = None
     if world > 1:   # the library's own communicator (NCCL inside librrtqx_b200.so); torch only moves the unique id
@@ -616,6 +620,7 @@ def main():
                        "nodes": args.nodes, "queries_per_gpu": args.queries, "radius": r,
                        "neighbours_per_step_rank0": K, "mean_neighbours": K / args.queries,
                        "parallelism": f"replicated tree x {world} query shards", "l2_flush_between_steps": True,
+                       "l2_flush": "256 MiB memset on the SAME stream as the library's kernels between timed iterations (scripts/exp_flush.py: write, write+read and copy flushes give the same timings)",
                        "count_gather": ("rrtqx_comm_allgather (NCCL inside the library) on the communicator's side stream; "
                                         "the timed steps include the wait for the last gather") if world > 1 else "none (one rank)"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,

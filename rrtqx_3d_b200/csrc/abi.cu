@@ -789,6 +789,7 @@ rrtqx_status rrtqx_sweep_result_flags(rrtqx_sweep_result *r, uint8_t *edge_flag,
   rrtqx_ctx *ctx = r->ctx;
   return guarded(ctx, [&] {
     bind_device(ctx);
+    sweep_result_rebuild_flags(ctx, r);
     from_device(ctx, edge_flag, r->edge_flag.p, (size_t)r->n_edges);
     from_device(ctx, node_flag, r->node_flag.p, (size_t)r->n_nodes);
     RQ_CUDA(cudaStreamSynchronize(ctx->stream));

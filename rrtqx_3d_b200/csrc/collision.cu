@@ -420,10 +420,14 @@ void edges_check(rrtqx_edges *E, const rrtqx_spheres *spheres, double robot_radi
       else
         ovf_dev = item_grid_run<false>(ctx, E->igrid, &E->igrid1, tab.rec, tab.thr, nullptr, n_live, (int)spheres->n, K, tree->pos.p,
                                        E->n_nodes, E->src.p, E->dst.p, n, par);
-      int32_t ovf = 0;
-      RQ_CUDA(cudaMemcpyAsync(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      // the overflow word travels to pinned memory behind the kernels; the flags are copied out right behind it, so
+      // the common case costs ONE synchronisation (an overflowed call marked nothing and is repeated below)
+      HostMail &M = host_mail(ctx);
+      RQ_CUDA(cudaMemcpyAsync(&M.h->aux[0], ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (!out_dev) from_device(ctx, collide_out, dout, (size_t)n);
       RQ_CUDA(cudaStreamSynchronize(st));
-      grid_done = ovf == 0;
+      grid_done = *(volatile int32_t *)&M.h->aux[0] == 0;
+      if (grid_done) return;   // the PhaseScope destructor records the end event
     }
     SphCoverBufs &cv = cover_bufs(ctx);
     const bool cached = b.grid_level == want_level && (!want_cover || cv.build_id == b.cover_id);

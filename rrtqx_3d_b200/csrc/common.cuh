@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -223,6 +224,43 @@ inline void post_launch(rrtqx_ctx *ctx, int n = 1) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     throw Error(RRTQX_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// Small results of a call (counts, flags) travel through one block of mapped pinned memory per context: the call's
+// last kernel stores them and then a call number, and the host spins on that word -- no copy operations, no stream
+// synchronisation (each of those costs 10-15 us on a call whose kernels take 40).  D2H copies of single words that
+// cannot come from a kernel use `aux` as their pinned target.
+struct HostMail {
+  struct Block { unsigned long long seq; long long v[6]; int32_t aux[2]; };
+  Block *h = nullptr, *d = nullptr;   // host / device views
+  unsigned long long seq = 0;         // calls issued
+  ~HostMail() { if (h) cudaFreeHost(h); }
+  void ensure() {
+    if (h) return;
+    RQ_CUDA(cudaHostAlloc((void **)&h, sizeof(Block), cudaHostAllocMapped));
+    RQ_CUDA(cudaHostGetDevicePointer((void **)&d, h, 0));
+    memset(h, 0, sizeof(Block));
+  }
+  // spin until the device has published call `want`; a stream query every few thousand spins turns a faulted launch
+  // into an error instead of a hang
+  void wait(cudaStream_t st, unsigned long long want) {
+    volatile unsigned long long *seqp = &h->seq;
+    for (unsigned spins = 0; *seqp != want; ++spins) {
+      if ((spins & 0xfff) == 0xfff) {
+        cudaError_t qe = cudaStreamQuery(st);
+        if (qe == cudaSuccess) break;
+        if (qe != cudaErrorNotReady) RQ_CUDA(qe);
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (*seqp != want) RQ_CUDA(cudaStreamSynchronize(st));
+  }
+};
+inline HostMail &host_mail(rrtqx_ctx *ctx) {
+  static const char tag = 0;
+  HostMail &m = ctx->scratch.get<HostMail>(&tag);
+  m.ensure();
+  return m;
 }
 
 // Input array that may live on host or device: returns a device pointer valid

@@ -65,7 +65,8 @@ struct rrtqx_sweep_result {
   rrtqx_ctx *ctx = nullptr;
   int64_t n_edges = 0, n_nodes = 0;
   int64_t n_edge_hits = 0, n_node_hits = 0, n_candidates = 0, n_pair_tests = 0;
-  rrtqx::DevBuf<uint8_t> edge_flag, node_flag;
+  rrtqx::DevBuf<uint8_t> edge_flag, node_flag;   // byte flags of the call in flight; zero again after sweep_finish
+  bool flags_clean = false;                      // flag arrays and statistics are all-zero (left so by sweep_finish)
   rrtqx::DevBuf<int32_t> edge_scan, node_scan, edge_list, node_list, scan_tmp;
   rrtqx::DevBuf<unsigned long long> stats;
   // obstacle table of the sweep
@@ -114,7 +115,9 @@ void obstacle_remove_sweep(rrtqx_edges *E, const rrtqx_spheres *S, int32_t ob_id
                            int64_t n_others, const uint8_t *edge_dist_inf, double robot_radius, double delta,
                            uint32_t flags, rrtqx_sweep_result *R);
 void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R);   // zeroed flag arrays for the current edge set
-void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R);           // flags -> ascending id lists + counts
+// flags -> ascending id lists + counts (one launch; cleans the flags); *extra_out = the device word *extra_dev
+void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R, const int32_t *extra_dev = nullptr, int32_t *extra_out = nullptr);
+void sweep_result_rebuild_flags(rrtqx_ctx *ctx, rrtqx_sweep_result *R);   // byte flags of the last result, from its lists
 // sweep2d.cu
 void edges_set_trajectories(rrtqx_edges *E, const int64_t *traj_ptr, const double *traj_xy);
 void edges_solve_trajectories(rrtqx_edges *E, double min_turn_radius);

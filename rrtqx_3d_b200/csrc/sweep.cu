@@ -513,112 +513,200 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
 }
 
 // ------------------------------------------------------- flag compaction
-// Ordered compaction of the byte-flag arrays into id lists without a per-element scan array: tile counts, a scan of
-// the tile counts, then each block ranks its own tile of SCAN_TILE flags (8 consecutive flags per thread) and writes
-// the ids in ascending order.
-// Both flag arrays (edges, nodes) in one launch per stage: blocks [0, tiles_a) work on array A, the rest on array B.
-__global__ void __launch_bounds__(SCAN_THREADS)
-flag_tile_sums2_kernel(const uint8_t *__restrict__ fa, int64_t na, int tiles_a, int32_t *__restrict__ sums_a,
-                       const uint8_t *__restrict__ fb, int64_t nb, int32_t *__restrict__ sums_b) {
+// Ordered compaction of the two byte-flag arrays (edges, nodes) into ascending id lists in ONE launch.  Tiles of
+// FC_TILE = 16384 flags are drawn from a ticket counter (so every predecessor of a tile is running or finished); a
+// block counts its tile, publishes the count, SUMS the published counts of all its predecessors (a few hundred words,
+// 256 per round trip, no chain of dependent look-backs) and writes its ids.  Tiles [0, tiles_a) belong to the edge
+// array, the rest to the node array, whose prefix restarts at tiles_a.
+//   * the kernel ZEROES every flag it found set: the arrays are clean again when the call returns, so the next
+//     call needs no 10 MB memset (rrtqx_sweep_result_flags rebuilds the byte view from the lists);
+//   * status words carry a call tag, ticket / completion counters only ever grow: nothing is reset between calls;
+//   * the last block to finish stores the totals, the sweep statistics (which it zeroes for the next call) and one
+//     optional extra word (the item grid's overflow flag) into the context's mapped mailbox and publishes the
+//     call number: the host spins on that word instead of three D2H copies and a stream synchronisation.
+constexpr int FC_THREADS = 256, FC_ITEMS = 16, FC_SUB = 4, FC_TILE = FC_THREADS * FC_ITEMS * FC_SUB;
+struct FlagCompactState {
+  unsigned long long ticket, done;   // tiles drawn / finished since the allocation of this state
+  int32_t totals[2];
+  uint32_t pad[2];
+};
+__device__ __forceinline__ unsigned long long fc_ld(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fc_st(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__global__ void __launch_bounds__(FC_THREADS)
+flag_compact_fused_kernel(uint8_t *__restrict__ fa, int64_t na, int tiles_a, int32_t *__restrict__ out_a,
+                          uint8_t *__restrict__ fb, int64_t nb, int tiles_b, int32_t *__restrict__ out_b,
+                          unsigned long long *__restrict__ status, FlagCompactState *__restrict__ state,
+                          unsigned long long ticket_base, uint32_t tag, unsigned long long *__restrict__ stats,
+                          const int32_t *__restrict__ extra, HostMail::Block *__restrict__ mail, unsigned long long seq) {
   __shared__ int32_t sm[33];
-  const bool second = (int)blockIdx.x >= tiles_a;
-  const uint8_t *flag = second ? fb : fa;
+  __shared__ int s_tile;
+  __shared__ int32_t s_prefix;
+  if (threadIdx.x == 0) { s_tile = (int)(atomicAdd(&state->ticket, 1ull) - ticket_base); s_prefix = 0; }
+  __syncthreads();
+  const int tile_g = s_tile;
+  const bool second = tile_g >= tiles_a;
+  const int first = second ? tiles_a : 0;
+  const int tile = tile_g - first;
+  uint8_t *flag = second ? fb : fa;
   const int64_t n = second ? nb : na;
-  const int tile = second ? blockIdx.x - tiles_a : blockIdx.x;
-  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-  int32_t cnt = 0;
-  if (base + SCAN_ITEMS <= n) {
-    const uint2 w = *reinterpret_cast<const uint2 *>(flag + base);
-    cnt = __popc(__vcmpne4(w.x, 0u) & 0x01010101u) + __popc(__vcmpne4(w.y, 0u) & 0x01010101u);
-  } else {
-    for (int k = 0; k < SCAN_ITEMS; ++k) cnt += (base + k < n && flag[base + k]) ? 1 : 0;
+  int32_t *out = second ? out_b : out_a;
+  const int64_t tbase = (int64_t)tile * FC_TILE + (int64_t)threadIdx.x * FC_ITEMS;   // + s * FC_THREADS * FC_ITEMS
+  uint32_t w[FC_SUB][4];
+  int32_t cnt[FC_SUB];
+#pragma unroll
+  for (int s = 0; s < FC_SUB; ++s) {
+    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
+    w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+    if (base + FC_ITEMS <= n) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(flag + base);
+      w[s][0] = v.x; w[s][1] = v.y; w[s][2] = v.z; w[s][3] = v.w;
+    } else {
+      for (int k = 0; k < FC_ITEMS; ++k)
+        if (base + k < n && flag[base + k]) w[s][k >> 2] |= 1u << (8 * (k & 3));
+    }
+  }
+  int32_t mine = 0;
+#pragma unroll
+  for (int s = 0; s < FC_SUB; ++s) {
+    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
+    if (w[s][0] | w[s][1] | w[s][2] | w[s][3]) {   // clean up behind ourselves
+      if (base + FC_ITEMS <= n) *reinterpret_cast<uint4 *>(flag + base) = make_uint4(0u, 0u, 0u, 0u);
+      else for (int k = 0; k < FC_ITEMS; ++k) if (base + k < n) flag[base + k] = 0;
+    }
+    cnt[s] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w[s][k] = __vcmpne4(w[s][k], 0u) & 0x01010101u; cnt[s] += __popc(w[s][k]); }
+    mine += cnt[s];
   }
   int32_t tot;
-  block_exclusive_scan<int32_t>(cnt, sm, &tot);
-  if (threadIdx.x == 0) (second ? sums_b : sums_a)[tile] = tot;
-}
-__global__ void __launch_bounds__(1024) flag_scan_sums2_kernel(int32_t *__restrict__ sums_a, int64_t tiles_a,
-                                                               int32_t *__restrict__ sums_b, int64_t tiles_b) {
-  __shared__ int32_t sm[33];
-  __shared__ int32_t carry_s;
-  int32_t *tile_sums = blockIdx.x ? sums_b : sums_a;
-  const int64_t n_tiles = blockIdx.x ? tiles_b : tiles_a;
-  if (threadIdx.x == 0) carry_s = 0;
+  block_exclusive_scan<int32_t>(mine, sm, &tot);
+  const unsigned long long hi = ((unsigned long long)tag << 32);
+  if (threadIdx.x == 0) fc_st(&status[tile_g], hi | (unsigned)tot);
+  // sum of the predecessors' counts: every thread takes one status word per round
+  int32_t part = 0;
+  for (int j0 = first; j0 < tile_g; j0 += FC_THREADS) {
+    const int idx = j0 + threadIdx.x;
+    if (idx < tile_g) {
+      unsigned long long sw;
+      do { sw = fc_ld(&status[idx]); } while ((uint32_t)(sw >> 32) != tag);
+      part += (int32_t)(uint32_t)sw;
+    }
+  }
+  if (tile > 0) {   // block-wide sum of part (uniform branch)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_prefix, part);
+  }
   __syncthreads();
-  for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
-    const int64_t i = base + threadIdx.x;
-    const int32_t v = (i < n_tiles) ? tile_sums[i] : 0;
-    int32_t tot;
-    const int32_t ex = block_exclusive_scan<int32_t>(v, sm, &tot);
-    const int32_t carry = carry_s;
-    if (i < n_tiles) tile_sums[i] = ex + carry;
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + tot;
-    __syncthreads();
+  const int32_t prefix = s_prefix;
+  if (threadIdx.x == 0 && tile == (second ? tiles_b : tiles_a) - 1) *(volatile int32_t *)&state->totals[second ? 1 : 0] = prefix + tot;
+  int32_t run = prefix;
+#pragma unroll
+  for (int s = 0; s < FC_SUB; ++s) {
+    int32_t stot;
+    int32_t pos = run + block_exclusive_scan<int32_t>(cnt[s], sm, &stot);
+    run += stot;
+    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
+    if (cnt[s]) {
+#pragma unroll
+      for (int k = 0; k < FC_ITEMS; ++k)
+        if ((w[s][k >> 2] >> (8 * (k & 3))) & 1u) out[pos++] = (int32_t)(base + k);
+    }
   }
-  if (threadIdx.x == 0) tile_sums[n_tiles] = carry_s;  // grand total
-}
-__global__ void __launch_bounds__(SCAN_THREADS)
-flag_compact2_kernel(const uint8_t *__restrict__ fa, int64_t na, int tiles_a, const int32_t *__restrict__ off_a,
-                     int32_t *__restrict__ out_a, const uint8_t *__restrict__ fb, int64_t nb,
-                     const int32_t *__restrict__ off_b, int32_t *__restrict__ out_b) {
-  __shared__ int32_t sm[33];
-  const bool second = (int)blockIdx.x >= tiles_a;
-  const uint8_t *flag = second ? fb : fa;
-  const int64_t n = second ? nb : na;
-  const int tile = second ? blockIdx.x - tiles_a : blockIdx.x;
-  int32_t *out = second ? out_b : out_a;
-  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-  unsigned char f[SCAN_ITEMS];
-  int32_t cnt = 0;
-  if (base + SCAN_ITEMS <= n) {
-    const uint2 w = *reinterpret_cast<const uint2 *>(flag + base);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { f[k] = (w.x >> (8 * k)) & 0xff; f[4 + k] = (w.y >> (8 * k)) & 0xff; }
-  } else {
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) f[k] = base + k < n ? flag[base + k] : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long prev = atomicAdd(&state->done, 1ull);
+    if (prev + 1ull == ticket_base + (unsigned long long)(tiles_a + tiles_b)) {   // last block of the call
+      __threadfence();
+      mail->v[0] = tiles_a ? *(volatile int32_t *)&state->totals[0] : 0;
+      mail->v[1] = tiles_b ? *(volatile int32_t *)&state->totals[1] : 0;
+      mail->v[2] = stats ? (long long)*(volatile unsigned long long *)&stats[0] : 0;
+      mail->v[3] = stats ? (long long)*(volatile unsigned long long *)&stats[1] : 0;
+      mail->v[4] = extra ? *(volatile const int32_t *)extra : 0;
+      if (stats) { stats[0] = 0ull; stats[1] = 0ull; }
+      __threadfence_system();
+      *(volatile unsigned long long *)&mail->seq = seq;
+      __threadfence_system();
+    }
   }
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) cnt += f[k] ? 1 : 0;
-  int32_t pos = block_exclusive_scan<int32_t>(cnt, sm, (int32_t *)nullptr) + (second ? off_b : off_a)[tile];
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k)
-    if (f[k]) out[pos++] = (int32_t)(base + k);
 }
 
-// Flags -> ascending id lists.  The lists are allocated for the worst case (every edge / node), so the three stages run
-// back to back without a host round trip in the middle; the counts are read once, at the end.
-void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
+// list -> byte flags (rrtqx_sweep_result_flags: the compaction leaves the flag arrays clean)
+__global__ void flags_from_list_kernel(const int32_t *__restrict__ list, int64_t n, uint8_t *__restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[list[i]] = 1;
+}
+
+struct FlagCompactBufs {   // per context
+  DevBuf<unsigned long long> status;
+  DevBuf<FlagCompactState> state;
+  unsigned long long ticket_base = 0;   // tiles of all earlier calls
+  uint32_t tag = 0;
+};
+static FlagCompactBufs &flag_compact_bufs(rrtqx_ctx *ctx) {
+  static const char tag = 0;
+  return ctx->scratch.get<FlagCompactBufs>(&tag);
+}
+
+// Flags -> ascending id lists + counts (+ one extra device word, returned in *extra_out).  The lists are allocated
+// for the worst case (every edge / node); one launch, results through the context's mailbox.
+void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R, const int32_t *extra_dev, int32_t *extra_out) {
   cudaStream_t st = ctx->stream;
-  static_assert(SCAN_ITEMS == 8, "the flag kernels read 8 flags per thread as one 64-bit word");
-  const int64_t et = (R->n_edges + SCAN_TILE - 1) / SCAN_TILE, nt = (R->n_nodes + SCAN_TILE - 1) / SCAN_TILE;
-  R->edge_scan.ensure((size_t)et + 2, st);  // tile offsets, [et] = total
-  R->node_scan.ensure((size_t)nt + 2, st);
+  const int64_t et = (R->n_edges + FC_TILE - 1) / FC_TILE, nt = (R->n_nodes + FC_TILE - 1) / FC_TILE;
   R->edge_list.ensure((size_t)R->n_edges + 1, st);
   R->node_list.ensure((size_t)R->n_nodes + 1, st);
-  if (et + nt > 0) {
-    flag_tile_sums2_kernel<<<(unsigned)(et + nt), SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_scan.p,
-                                                                        R->node_flag.p, R->n_nodes, R->node_scan.p);
-    flag_scan_sums2_kernel<<<2, 1024, 0, st>>>(R->edge_scan.p, et, R->node_scan.p, nt);
-    flag_compact2_kernel<<<(unsigned)(et + nt), SCAN_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_scan.p,
-                                                                      R->edge_list.p, R->node_flag.p, R->n_nodes,
-                                                                      R->node_scan.p, R->node_list.p);
-    post_launch(ctx, 3);
-  } else {
-    RQ_CUDA(cudaMemsetAsync(R->edge_scan.p, 0, sizeof(int32_t), st));
-    RQ_CUDA(cudaMemsetAsync(R->node_scan.p, 0, sizeof(int32_t), st));
+  if (et + nt == 0) {
+    RQ_CUDA(cudaStreamSynchronize(st));
+    R->n_edge_hits = R->n_node_hits = R->n_candidates = R->n_pair_tests = 0;
+    if (extra_out) *extra_out = 0;
+    R->flags_clean = true;
+    return;
   }
-  int32_t ne_hits = 0, nn_hits = 0;
-  unsigned long long stats[2] = {0, 0};
-  RQ_CUDA(cudaMemcpyAsync(&ne_hits, R->edge_scan.p + et, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  RQ_CUDA(cudaMemcpyAsync(&nn_hits, R->node_scan.p + nt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  RQ_CUDA(cudaMemcpyAsync(stats, R->stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
-  RQ_CUDA(cudaStreamSynchronize(st));
-  R->n_edge_hits = ne_hits;
-  R->n_node_hits = nn_hits;
-  R->n_candidates = (int64_t)stats[0];
-  R->n_pair_tests = (int64_t)stats[1];
+  FlagCompactBufs &B = flag_compact_bufs(ctx);
+  if (!B.state.p) {
+    B.state.ensure(1, st);
+    RQ_CUDA(cudaMemsetAsync(B.state.p, 0, sizeof(FlagCompactState), st));
+    B.ticket_base = 0;
+  }
+  if ((size_t)(et + nt) > B.status.cap || B.tag == 0xffffffffu) {   // new (uninitialised) words, or the tag wraps
+    B.status.ensure((size_t)(et + nt), st);
+    RQ_CUDA(cudaMemsetAsync(B.status.p, 0, B.status.cap * sizeof(unsigned long long), st));
+    B.tag = 0;
+  }
+  HostMail &M = host_mail(ctx);
+  const unsigned long long seq = ++M.seq;
+  ++B.tag;
+  flag_compact_fused_kernel<<<(unsigned)(et + nt), FC_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_list.p,
+                                                                        R->node_flag.p, R->n_nodes, (int)nt, R->node_list.p,
+                                                                        B.status.p, B.state.p, B.ticket_base, B.tag, R->stats.p,
+                                                                        extra_dev, M.d, seq);
+  post_launch(ctx);
+  B.ticket_base += (unsigned long long)(et + nt);
+  M.wait(st, seq);
+  R->n_edge_hits = M.h->v[0];
+  R->n_node_hits = M.h->v[1];
+  R->n_candidates = M.h->v[2];
+  R->n_pair_tests = M.h->v[3];
+  if (extra_out) *extra_out = (int32_t)M.h->v[4];
+  R->flags_clean = true;
+}
+
+// Byte-flag view of the last result, rebuilt from the id lists (the compaction cleaned the arrays); the arrays are
+// dirty afterwards and the next sweep clears them with a memset.
+void sweep_result_rebuild_flags(rrtqx_ctx *ctx, rrtqx_sweep_result *R) {
+  cudaStream_t st = ctx->stream;
+  if (!R->flags_clean) return;   // still hold the flags of the last call (or nothing was ever swept)
+  if (R->n_edge_hits > 0) flags_from_list_kernel<<<div_up(R->n_edge_hits, 256), 256, 0, st>>>(R->edge_list.p, R->n_edge_hits, R->edge_flag.p);
+  if (R->n_node_hits > 0) flags_from_list_kernel<<<div_up(R->n_node_hits, 256), 256, 0, st>>>(R->node_list.p, R->n_node_hits, R->node_flag.p);
+  post_launch(ctx, 2);
+  R->flags_clean = false;
 }
 
 void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
@@ -627,12 +715,18 @@ void sweep_prepare_result(rrtqx_edges *E, rrtqx_sweep_result *R) {
   R->ctx = ctx;
   R->n_edges = E->n_edges;
   R->n_nodes = E->n_nodes;
+  const uint8_t *pe = R->edge_flag.p, *pn = R->node_flag.p;
+  const unsigned long long *ps = R->stats.p;
   R->edge_flag.ensure((size_t)E->n_edges + 1, st);
   R->node_flag.ensure((size_t)E->n_nodes + 1, st);
   R->stats.ensure(4, st);
-  RQ_CUDA(cudaMemsetAsync(R->edge_flag.p, 0, (size_t)E->n_edges + 1, st));
-  RQ_CUDA(cudaMemsetAsync(R->node_flag.p, 0, (size_t)E->n_nodes + 1, st));
-  RQ_CUDA(cudaMemsetAsync(R->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  // the compaction leaves flags and statistics zeroed: clear only new allocations and arrays left dirty by a failed
+  // call or by rrtqx_sweep_result_flags (whole capacity, so a later, larger edge set finds zeros too)
+  const bool dirty = !R->flags_clean;
+  if (dirty || pe != R->edge_flag.p) RQ_CUDA(cudaMemsetAsync(R->edge_flag.p, 0, R->edge_flag.cap, st));
+  if (dirty || pn != R->node_flag.p) RQ_CUDA(cudaMemsetAsync(R->node_flag.p, 0, R->node_flag.cap, st));
+  if (dirty || ps != R->stats.p) RQ_CUDA(cudaMemsetAsync(R->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  R->flags_clean = false;   // until sweep_finish has run
 }
 
 void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *ob_ids, int64_t n_obs,
@@ -669,9 +763,8 @@ void obstacle_add_sweep(rrtqx_edges *E, const rrtqx_spheres *S, const int32_t *o
                                        E->tree->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par);
       // the overflow flag (more work units than the list holds: huge obstacles) is read together with the counts;
       // on overflow nothing was marked and the edge-centric kernels repeat the sweep (below)
-      sweep_finish(ctx, R);
       int32_t ovf = 0;
-      RQ_CUDA(cudaMemcpy(&ovf, ovf_dev, sizeof(int32_t), cudaMemcpyDeviceToHost));
+      sweep_finish(ctx, R, ovf_dev, &ovf);
       grid_done = ovf == 0;
       no_stats = true;
       if (grid_done) { R->n_candidates = -1; R->n_pair_tests = -1; return; }
