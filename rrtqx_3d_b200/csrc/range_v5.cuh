@@ -56,6 +56,30 @@ __device__ __forceinline__ double4 ldg256(const double4 *p) {
   return v;
 }
 
+// Result stores.  The lists are written once and never read by the kernel: streaming stores (evict-first) keep the
+// 5 GB of output from pushing the 64 MB of records / cell starts out of L2.
+#ifndef V5_STORE_MODE
+#define V5_STORE_MODE 0
+#endif
+__device__ __forceinline__ void v5_st(int32_t *p, int32_t v) {
+#if V5_STORE_MODE == 1
+  __stcs(p, v);
+#elif V5_STORE_MODE == 2
+  __stwt(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void v5_st(double *p, double v) {
+#if V5_STORE_MODE == 1
+  __stcs(p, v);
+#elif V5_STORE_MODE == 2
+  __stwt(p, v);
+#else
+  *p = v;
+#endif
+}
+
 // double -> float rounded up (host twin: nextafter of the nearest conversion when it fell below)
 __host__ __device__ __forceinline__ float f32_up(double x) {
 #ifdef __CUDA_ARCH__
@@ -184,8 +208,8 @@ __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, uns
     for (int u = 0; u < U; ++u) fetch(lds16(sbuf_k + 2u * (unsigned)(h0 + 32 * u)), node[u], p[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      oi[h0 + 32 * u] = node[u];
-      if (od) od[h0 + 32 * u] = __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w));
+      v5_st(oi + h0 + 32 * u, node[u]);
+      if (od) v5_st(od + h0 + 32 * u, __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w)));
     }
   }
   // last, partial group: same shape (all loads in flight before the first use), predicated, and only as many rows
@@ -204,8 +228,8 @@ __device__ __forceinline__ void v5_flush(const GridView &g, const double *q, uns
 #pragma unroll
     for (int u = 0; u < R; ++u)
       if (h0 + 32 * u < n) {
-        oi[h0 + 32 * u] = node[u];
-        if (od) od[h0 + 32 * u] = __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w));
+        v5_st(oi + h0 + 32 * u, node[u]);
+        if (od) v5_st(od + h0 + 32 * u, __dsqrt_rn(sqdist<D>(q, p[u].x, p[u].y, p[u].z, p[u].w)));
       }
   };
   const int rem = n - n_full;

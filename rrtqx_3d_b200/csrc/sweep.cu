@@ -513,129 +513,118 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
 }
 
 // ------------------------------------------------------- flag compaction
-// Ordered compaction of the two byte-flag arrays (edges, nodes) into ascending id lists in ONE launch.  Tiles of
-// FC_TILE = 16384 flags are drawn from a ticket counter (so every predecessor of a tile is running or finished); a
-// block counts its tile, publishes the count, SUMS the published counts of all its predecessors (a few hundred words,
-// 256 per round trip, no chain of dependent look-backs) and writes its ids.  Tiles [0, tiles_a) belong to the edge
-// array, the rest to the node array, whose prefix restarts at tiles_a.
-//   * the kernel ZEROES every flag it found set: the arrays are clean again when the call returns, so the next
-//     call needs no 10 MB memset (rrtqx_sweep_result_flags rebuilds the byte view from the lists);
-//   * status words carry a call tag, ticket / completion counters only ever grow: nothing is reset between calls;
-//   * the last block to finish stores the totals, the sweep statistics (which it zeroes for the next call) and one
-//     optional extra word (the item grid's overflow flag) into the context's mapped mailbox and publishes the
+// Ordered compaction of the two byte-flag arrays (edges, nodes) into ascending id lists: tile counts, then one launch
+// in which every block sums the counts of its predecessors itself (a few thousand words, all loads in flight at once:
+// cheaper than a separate scan launch and than a single-pass look-back, whose spin / ticket traffic measured 40 us
+// here), ranks its tile in shared memory and writes the ids coalesced.  Tiles [0, tiles_a) belong to the edge array,
+// the rest to the node array, whose prefix restarts at tiles_a.
+//   * the second kernel ZEROES every flag it found set: the arrays are clean again when the call returns, so the
+//     next call needs no 10 MB memset (rrtqx_sweep_result_flags rebuilds the byte view from the lists);
+//   * a one-warp kernel behind it stores the totals, the sweep statistics (which it zeroes for the next call) and
+//     one optional extra word (the item grid's overflow flag) into the context's mapped mailbox and publishes the
 //     call number: the host spins on that word instead of three D2H copies and a stream synchronisation.
-constexpr int FC_THREADS = 256, FC_ITEMS = 16, FC_SUB = 4, FC_TILE = FC_THREADS * FC_ITEMS * FC_SUB;
-struct FlagCompactState {
-  unsigned long long ticket, done;   // tiles drawn / finished since the allocation of this state
-  int32_t totals[2];
-  uint32_t pad[2];
-};
-__device__ __forceinline__ unsigned long long fc_ld(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fc_st(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+constexpr int FC_THREADS = 256, FC_ITEMS = 16, FC_TILE = FC_THREADS * FC_ITEMS;
+__device__ __forceinline__ int fc_load(const uint8_t *__restrict__ flag, int64_t base, int64_t n, uint32_t (&w)[4]) {
+  w[0] = w[1] = w[2] = w[3] = 0u;
+  if (base + FC_ITEMS <= n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(flag + base);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
+    for (int k = 0; k < FC_ITEMS; ++k)
+      if (base + k < n && flag[base + k]) w[k >> 2] |= 1u << (8 * (k & 3));
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { w[k] = __vcmpne4(w[k], 0u) & 0x01010101u; cnt += __popc(w[k]); }
+  return cnt;
 }
 __global__ void __launch_bounds__(FC_THREADS)
-flag_compact_fused_kernel(uint8_t *__restrict__ fa, int64_t na, int tiles_a, int32_t *__restrict__ out_a,
-                          uint8_t *__restrict__ fb, int64_t nb, int tiles_b, int32_t *__restrict__ out_b,
-                          unsigned long long *__restrict__ status, FlagCompactState *__restrict__ state,
-                          unsigned long long ticket_base, uint32_t tag, unsigned long long *__restrict__ stats,
-                          const int32_t *__restrict__ extra, HostMail::Block *__restrict__ mail, unsigned long long seq) {
-  __shared__ int32_t sm[33];
-  __shared__ int s_tile;
-  __shared__ int32_t s_prefix;
-  if (threadIdx.x == 0) { s_tile = (int)(atomicAdd(&state->ticket, 1ull) - ticket_base); s_prefix = 0; }
+flag_tile_counts_kernel(const uint8_t *__restrict__ fa, int64_t na, int tiles_a, const uint8_t *__restrict__ fb, int64_t nb,
+                        int32_t *__restrict__ counts) {
+  __shared__ int32_t sm[FC_THREADS / 32];
+  const bool second = (int)blockIdx.x >= tiles_a;
+  const int tile = second ? blockIdx.x - tiles_a : blockIdx.x;
+  uint32_t w[4];
+  int32_t cnt = fc_load(second ? fb : fa, (int64_t)tile * FC_TILE + (int64_t)threadIdx.x * FC_ITEMS, second ? nb : na, w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
   __syncthreads();
-  const int tile_g = s_tile;
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < FC_THREADS / 32; ++k) t += sm[k];
+    counts[blockIdx.x] = t;
+  }
+}
+__device__ __forceinline__ void sweep_publish(int32_t tot_a, int32_t tot_b, int tiles_a, int tiles_b,
+                                              unsigned long long *__restrict__ stats, const int32_t *__restrict__ extra,
+                                              HostMail::Block *__restrict__ mail, unsigned long long seq) {
+  mail->v[0] = tiles_a ? tot_a : 0;
+  mail->v[1] = tiles_b ? tot_b : 0;
+  mail->v[2] = stats ? (long long)*(volatile unsigned long long *)&stats[0] : 0;
+  mail->v[3] = stats ? (long long)*(volatile unsigned long long *)&stats[1] : 0;
+  mail->v[4] = extra ? *(volatile const int32_t *)extra : 0;
+  if (stats) { stats[0] = 0ull; stats[1] = 0ull; }
+  __threadfence_system();
+  *(volatile unsigned long long *)&mail->seq = seq;
+}
+__global__ void __launch_bounds__(FC_THREADS, 8)
+flag_compact_kernel(uint8_t *__restrict__ fa, int64_t na, int tiles_a, int32_t *__restrict__ out_a,
+                    uint8_t *__restrict__ fb, int64_t nb, int tiles_b, int32_t *__restrict__ out_b,
+                    const int32_t *__restrict__ counts, int32_t *__restrict__ totals /* [2] totals, [2] done counter */,
+                    unsigned long long *__restrict__ stats, const int32_t *__restrict__ extra,
+                    HostMail::Block *__restrict__ mail, unsigned long long seq) {
+  __shared__ int32_t sm[33];
+  __shared__ int32_t s_prefix;
+  __shared__ int32_t s_ids[FC_TILE];
+  const int tile_g = blockIdx.x;
   const bool second = tile_g >= tiles_a;
   const int first = second ? tiles_a : 0;
   const int tile = tile_g - first;
   uint8_t *flag = second ? fb : fa;
   const int64_t n = second ? nb : na;
   int32_t *out = second ? out_b : out_a;
-  const int64_t tbase = (int64_t)tile * FC_TILE + (int64_t)threadIdx.x * FC_ITEMS;   // + s * FC_THREADS * FC_ITEMS
-  uint32_t w[FC_SUB][4];
-  int32_t cnt[FC_SUB];
-#pragma unroll
-  for (int s = 0; s < FC_SUB; ++s) {
-    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
-    w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
-    if (base + FC_ITEMS <= n) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(flag + base);
-      w[s][0] = v.x; w[s][1] = v.y; w[s][2] = v.z; w[s][3] = v.w;
-    } else {
-      for (int k = 0; k < FC_ITEMS; ++k)
-        if (base + k < n && flag[base + k]) w[s][k >> 2] |= 1u << (8 * (k & 3));
-    }
-  }
-  int32_t mine = 0;
-#pragma unroll
-  for (int s = 0; s < FC_SUB; ++s) {
-    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
-    if (w[s][0] | w[s][1] | w[s][2] | w[s][3]) {   // clean up behind ourselves
-      if (base + FC_ITEMS <= n) *reinterpret_cast<uint4 *>(flag + base) = make_uint4(0u, 0u, 0u, 0u);
-      else for (int k = 0; k < FC_ITEMS; ++k) if (base + k < n) flag[base + k] = 0;
-    }
-    cnt[s] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { w[s][k] = __vcmpne4(w[s][k], 0u) & 0x01010101u; cnt[s] += __popc(w[s][k]); }
-    mine += cnt[s];
-  }
-  int32_t tot;
-  block_exclusive_scan<int32_t>(mine, sm, &tot);
-  const unsigned long long hi = ((unsigned long long)tag << 32);
-  if (threadIdx.x == 0) fc_st(&status[tile_g], hi | (unsigned)tot);
-  // sum of the predecessors' counts: every thread takes one status word per round
+  if (threadIdx.x == 0) s_prefix = 0;
+  // sum of the predecessors' counts: independent loads, all in flight before the first use
   int32_t part = 0;
-  for (int j0 = first; j0 < tile_g; j0 += FC_THREADS) {
-    const int idx = j0 + threadIdx.x;
-    if (idx < tile_g) {
-      unsigned long long sw;
-      do { sw = fc_ld(&status[idx]); } while ((uint32_t)(sw >> 32) != tag);
-      part += (int32_t)(uint32_t)sw;
-    }
+  for (int j = first + (int)threadIdx.x; j < tile_g; j += FC_THREADS) part += counts[j];
+  const int64_t base = (int64_t)tile * FC_TILE + (int64_t)threadIdx.x * FC_ITEMS;
+  uint32_t w[4];
+  const int32_t cnt = fc_load(flag, base, n, w);
+  if (cnt) {   // clean up behind ourselves
+    if (base + FC_ITEMS <= n) *reinterpret_cast<uint4 *>(flag + base) = make_uint4(0u, 0u, 0u, 0u);
+    else for (int k = 0; k < FC_ITEMS; ++k) if (base + k < n) flag[base + k] = 0;
   }
-  if (tile > 0) {   // block-wide sum of part (uniform branch)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_prefix, part);
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+  int32_t tot;
+  const int32_t ex = block_exclusive_scan<int32_t>(cnt, sm, &tot);   // (its barriers order the s_prefix initialisation)
+  if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_prefix, part);
+  {
+    int32_t p = ex;
+#pragma unroll
+    for (int k = 0; k < FC_ITEMS; ++k)
+      if ((w[k >> 2] >> (8 * (k & 3))) & 1u) s_ids[p++] = (int32_t)(base + k);
   }
   __syncthreads();
   const int32_t prefix = s_prefix;
-  if (threadIdx.x == 0 && tile == (second ? tiles_b : tiles_a) - 1) *(volatile int32_t *)&state->totals[second ? 1 : 0] = prefix + tot;
-  int32_t run = prefix;
-#pragma unroll
-  for (int s = 0; s < FC_SUB; ++s) {
-    int32_t stot;
-    int32_t pos = run + block_exclusive_scan<int32_t>(cnt[s], sm, &stot);
-    run += stot;
-    const int64_t base = tbase + (int64_t)s * (FC_THREADS * FC_ITEMS);
-    if (cnt[s]) {
-#pragma unroll
-      for (int k = 0; k < FC_ITEMS; ++k)
-        if ((w[s][k >> 2] >> (8 * (k & 3))) & 1u) out[pos++] = (int32_t)(base + k);
-    }
-  }
+  if (threadIdx.x == 0 && tile == (second ? tiles_b : tiles_a) - 1) totals[second ? 1 : 0] = prefix + tot;
+  for (int j = threadIdx.x; j < tot; j += FC_THREADS) out[prefix + j] = s_ids[j];
+  // the last block to finish publishes the call's small results (and resets the counter for the next call)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned long long prev = atomicAdd(&state->done, 1ull);
-    if (prev + 1ull == ticket_base + (unsigned long long)(tiles_a + tiles_b)) {   // last block of the call
+    if (atomicAdd(&totals[2], 1) == tiles_a + tiles_b - 1) {
       __threadfence();
-      mail->v[0] = tiles_a ? *(volatile int32_t *)&state->totals[0] : 0;
-      mail->v[1] = tiles_b ? *(volatile int32_t *)&state->totals[1] : 0;
-      mail->v[2] = stats ? (long long)*(volatile unsigned long long *)&stats[0] : 0;
-      mail->v[3] = stats ? (long long)*(volatile unsigned long long *)&stats[1] : 0;
-      mail->v[4] = extra ? *(volatile const int32_t *)extra : 0;
-      if (stats) { stats[0] = 0ull; stats[1] = 0ull; }
-      __threadfence_system();
-      *(volatile unsigned long long *)&mail->seq = seq;
-      __threadfence_system();
+      totals[2] = 0;
+      sweep_publish(*(volatile int32_t *)&totals[0], *(volatile int32_t *)&totals[1], tiles_a, tiles_b, stats, extra, mail, seq);
     }
   }
+}
+__global__ void sweep_publish_kernel(unsigned long long *__restrict__ stats, const int32_t *__restrict__ extra,
+                                     HostMail::Block *__restrict__ mail, unsigned long long seq) {   // empty edge set
+  if (threadIdx.x == 0) sweep_publish(0, 0, 0, 0, stats, extra, mail, seq);
 }
 
 // list -> byte flags (rrtqx_sweep_result_flags: the compaction leaves the flag arrays clean)
@@ -645,10 +634,7 @@ __global__ void flags_from_list_kernel(const int32_t *__restrict__ list, int64_t
 }
 
 struct FlagCompactBufs {   // per context
-  DevBuf<unsigned long long> status;
-  DevBuf<FlagCompactState> state;
-  unsigned long long ticket_base = 0;   // tiles of all earlier calls
-  uint32_t tag = 0;
+  DevBuf<int32_t> counts, totals;
 };
 static FlagCompactBufs &flag_compact_bufs(rrtqx_ctx *ctx) {
   static const char tag = 0;
@@ -656,39 +642,31 @@ static FlagCompactBufs &flag_compact_bufs(rrtqx_ctx *ctx) {
 }
 
 // Flags -> ascending id lists + counts (+ one extra device word, returned in *extra_out).  The lists are allocated
-// for the worst case (every edge / node); one launch, results through the context's mailbox.
+// for the worst case (every edge / node); three launches back to back, results through the context's mailbox.
 void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R, const int32_t *extra_dev, int32_t *extra_out) {
   cudaStream_t st = ctx->stream;
   const int64_t et = (R->n_edges + FC_TILE - 1) / FC_TILE, nt = (R->n_nodes + FC_TILE - 1) / FC_TILE;
   R->edge_list.ensure((size_t)R->n_edges + 1, st);
   R->node_list.ensure((size_t)R->n_nodes + 1, st);
-  if (et + nt == 0) {
-    RQ_CUDA(cudaStreamSynchronize(st));
-    R->n_edge_hits = R->n_node_hits = R->n_candidates = R->n_pair_tests = 0;
-    if (extra_out) *extra_out = 0;
-    R->flags_clean = true;
-    return;
-  }
   FlagCompactBufs &B = flag_compact_bufs(ctx);
-  if (!B.state.p) {
-    B.state.ensure(1, st);
-    RQ_CUDA(cudaMemsetAsync(B.state.p, 0, sizeof(FlagCompactState), st));
-    B.ticket_base = 0;
-  }
-  if ((size_t)(et + nt) > B.status.cap || B.tag == 0xffffffffu) {   // new (uninitialised) words, or the tag wraps
-    B.status.ensure((size_t)(et + nt), st);
-    RQ_CUDA(cudaMemsetAsync(B.status.p, 0, B.status.cap * sizeof(unsigned long long), st));
-    B.tag = 0;
+  B.counts.ensure((size_t)(et + nt) + 1, st);
+  if (!B.totals.p) {
+    B.totals.ensure(4, st);
+    RQ_CUDA(cudaMemsetAsync(B.totals.p, 0, 4 * sizeof(int32_t), st));   // [2]: blocks finished (reset by the last one)
   }
   HostMail &M = host_mail(ctx);
   const unsigned long long seq = ++M.seq;
-  ++B.tag;
-  flag_compact_fused_kernel<<<(unsigned)(et + nt), FC_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_list.p,
-                                                                        R->node_flag.p, R->n_nodes, (int)nt, R->node_list.p,
-                                                                        B.status.p, B.state.p, B.ticket_base, B.tag, R->stats.p,
-                                                                        extra_dev, M.d, seq);
-  post_launch(ctx);
-  B.ticket_base += (unsigned long long)(et + nt);
+  if (et + nt > 0) {
+    flag_tile_counts_kernel<<<(unsigned)(et + nt), FC_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->node_flag.p,
+                                                                        R->n_nodes, B.counts.p);
+    flag_compact_kernel<<<(unsigned)(et + nt), FC_THREADS, 0, st>>>(R->edge_flag.p, R->n_edges, (int)et, R->edge_list.p,
+                                                                    R->node_flag.p, R->n_nodes, (int)nt, R->node_list.p,
+                                                                    B.counts.p, B.totals.p, R->stats.p, extra_dev, M.d, seq);
+    post_launch(ctx, 2);
+  } else {
+    sweep_publish_kernel<<<1, 32, 0, st>>>(R->stats.p, extra_dev, M.d, seq);
+    post_launch(ctx);
+  }
   M.wait(st, seq);
   R->n_edge_hits = M.h->v[0];
   R->n_node_hits = M.h->v[1];
