@@ -80,6 +80,7 @@ struct rrtqx_sweep_result {
   rrtqx::DevBuf<int32_t> ids_stage, ids_stage2;
   rrtqx::DevBuf<uint8_t> inf_stage;
   rrtqx::DevBuf<unsigned char> filt2d;  // start-node filters of the Otte / Dubins sweeps (sweep2d.cu)
+  rrtqx::DevBuf<int32_t> cand2d, cand2d_n;  // items admitted by the start-node filters of a call with few obstacles
 };
 
 namespace rrtqx {

@@ -86,32 +86,70 @@ struct ListedObstacles {  // the obstacles of the call, each with the start-node
 #ifndef SWEEP2D_MINB
 #define SWEEP2D_MINB 6  // as DUBINS_MINB (polygon.cu): latency-bound FP64 chains, 48 warps per SM (16.7 -> 10.5 ms on the C4 graph)
 #endif
+constexpr int SWEEP2D_SELECT_MAX_OBS = 8;  // more listed obstacles admit nearly every item: no list
+// Few listed obstacles (the planner's call: ONE): the start-node filter admits a few per cent of the items, so a
+// thread-per-item pass lists them first and the warp-per-item kernels below run over that list only (a device-side
+// count, persistent warps) instead of spending a warp on every item of the graph.
+// MODE 0: addNewObstacle items (out-edges, then parent edges), any of the n_f filters; MODE 1: removeObstacle edges
+// (edge.dist == Inf only), filter 0.
+template <int D, int MODE>
+__global__ void __launch_bounds__(256)
+sweep2d_select_kernel(const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src, int64_t n_edges,
+                      const int32_t *__restrict__ parent, const uint8_t *__restrict__ edge_dist_inf,
+                      const Sweep2dFilter *__restrict__ filt, int n_f, int32_t *__restrict__ cand, int32_t *__restrict__ n_cand) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t items = MODE == 0 ? n_edges + n_nodes : n_edges;
+  bool keep = false;
+  if (i < items) {
+    int v;
+    bool live = true;
+    if (i >= n_edges) { v = (int)(i - n_edges); live = parent && parent[v] >= 0; }
+    else { v = src[i]; if (MODE == 1) live = edge_dist_inf[i] != 0; }
+    if (live) {
+      const double4 a = pos[v];
+      for (int k = 0; k < n_f && !keep; ++k) keep = sweep2d_candidate<D>(filt[k], a, v);
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, keep);
+  if (m) {
+    int base = 0;
+    if (lane_id() == 0) base = atomicAdd(n_cand, __popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (keep) cand[base + __popc(m & lanemask_lt())] = (int32_t)i;
+  }
+}
+
 // addNewObstacle: item i < n_edges is out-edge i (src[i] -> dst[i]); item n_edges + v is the parent edge of node v.
+// cand == nullptr: one warp per item of the graph; otherwise persistent warps over the listed items.
 template <int D>
 __global__ void __launch_bounds__(256, SWEEP2D_MINB)
 add_sweep_2d_kernel(PolyView P, const double4 *__restrict__ pos, int64_t n_nodes, const int32_t *__restrict__ src,
                     const int32_t *__restrict__ dst, int64_t n_edges, const int32_t *__restrict__ parent,
                     const int64_t *__restrict__ tptr, const double *__restrict__ traj, const int32_t *__restrict__ ids,
                     const Sweep2dFilter *__restrict__ filt, int n_obs, double rho, double rho_coarse,
-                    uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= n_edges + n_nodes) return;
-  int v, w;
-  if (i >= n_edges) {
-    v = (int)(i - n_edges);
-    w = parent ? parent[v] : -1;
-    if (w < 0) return;  // !rrtParentUsed (:3164)
-  } else {
-    v = src[i];
-    w = dst[i];
-  }
-  const double4 a = pos[v], b = pos[w];
-  const ListedObstacles<D> sel{ids, filt, n_obs, a, v};
-  // the obstacles of an add sweep count as active (ob.obstacleUnused = false, :3129)
-  const bool hit = dubins_collide_warp(P, true, sel, a.x, a.y, b.x, b.y, traj, tptr[i], tptr[i + 1], rho, rho_coarse);
-  if (hit && lane_id() == 0) {
-    if (i >= n_edges) node_flag[v] = 1;  // :3164-3177 orphan
-    else edge_flag[i] = 1;               // :3156-3158 edge.dist = Inf
+                    uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag,
+                    const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand) {
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = cand ? (int64_t)*n_cand : n_edges + n_nodes;
+  for (int64_t k = w0; k < total; k += n_w) {
+    const int64_t i = cand ? (int64_t)cand[k] : k;
+    int v, w;
+    if (i >= n_edges) {
+      v = (int)(i - n_edges);
+      w = parent ? parent[v] : -1;
+      if (w < 0) continue;  // !rrtParentUsed (:3164)
+    } else {
+      v = src[i];
+      w = dst[i];
+    }
+    const double4 a = pos[v], b = pos[w];
+    const ListedObstacles<D> sel{ids, filt, n_obs, a, v};
+    // the obstacles of an add sweep count as active (ob.obstacleUnused = false, :3129)
+    const bool hit = dubins_collide_warp(P, true, sel, a.x, a.y, b.x, b.y, traj, tptr[i], tptr[i + 1], rho, rho_coarse);
+    if (hit && lane_id() == 0) {
+      if (i >= n_edges) node_flag[v] = 1;  // :3164-3177 orphan
+      else edge_flag[i] = 1;               // :3156-3158 edge.dist = Inf
+    }
   }
 }
 
@@ -122,19 +160,23 @@ remove_sweep_2d_kernel(PolyView P, const double4 *__restrict__ pos, const int32_
                        const int32_t *__restrict__ dst, int64_t n_edges, const uint8_t *__restrict__ edge_dist_inf,
                        const int64_t *__restrict__ tptr, const double *__restrict__ traj, const int32_t *__restrict__ ids,
                        const Sweep2dFilter *__restrict__ filt, int n_ids, double rho, double rho_coarse,
-                       uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag) {
-  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (e >= n_edges) return;
-  if (!edge_dist_inf[e]) return;  // neighborEdge.dist == Inf (:3228)
-  const int v = src[e], w = dst[e];
-  const double4 a = pos[v], b = pos[w];
-  const ListedObstacles<D> removed{ids, filt, 1, a, v};
-  if (!dubins_collide_warp(P, true, removed, a.x, a.y, b.x, b.y, traj, tptr[e], tptr[e + 1], rho, rho_coarse)) return;
-  const ListedObstacles<D> others{ids + 1, nullptr, n_ids - 1, a, v};  // :3234-3246
-  if (dubins_collide_warp(P, true, others, a.x, a.y, b.x, b.y, traj, tptr[e], tptr[e + 1], rho, rho_coarse)) return;
-  if (lane_id() == 0) {  // :3249-3264
-    edge_flag[e] = 1;
-    node_flag[v] = 1;
+                       uint8_t *__restrict__ edge_flag, uint8_t *__restrict__ node_flag,
+                       const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand) {
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = cand ? (int64_t)*n_cand : n_edges;
+  for (int64_t k = w0; k < total; k += n_w) {
+    const int64_t e = cand ? (int64_t)cand[k] : k;
+    if (!edge_dist_inf[e]) continue;  // neighborEdge.dist == Inf (:3228)
+    const int v = src[e], w = dst[e];
+    const double4 a = pos[v], b = pos[w];
+    const ListedObstacles<D> removed{ids, filt, 1, a, v};
+    if (!dubins_collide_warp(P, true, removed, a.x, a.y, b.x, b.y, traj, tptr[e], tptr[e + 1], rho, rho_coarse)) continue;
+    const ListedObstacles<D> others{ids + 1, nullptr, n_ids - 1, a, v};  // :3234-3246
+    if (dubins_collide_warp(P, true, others, a.x, a.y, b.x, b.y, traj, tptr[e], tptr[e + 1], rho, rho_coarse)) continue;
+    if (lane_id() == 0) {  // :3249-3264
+      edge_flag[e] = 1;
+      node_flag[v] = 1;
+    }
   }
 }
 
@@ -257,12 +299,30 @@ void obstacle_add_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *Pg, const int32
   if (n_obs > 0 && items > 0) {
     const double rho_coarse = robot_radius + 2 * min_turn_radius;  // DRRT_DubinsEdge_functions.jl:758
     const int32_t *par = E->has_parent ? E->parent.p : nullptr;
-    const unsigned blocks = (unsigned)div_up(items * 32, 256);
+    // few obstacles: list the admitted items first (thread per item), then persistent warps over the list
+    const bool two_stage = n_obs <= SWEEP2D_SELECT_MAX_OBS && items < ((int64_t)1 << 31);
+    const int32_t *cand = nullptr, *n_cand = nullptr;
+    unsigned blocks = (unsigned)div_up(items * 32, 256);
+    if (two_stage) {
+      R->cand2d.ensure((size_t)items + 1, st);
+      R->cand2d_n.ensure(4, st);
+      RQ_CUDA(cudaMemsetAsync(R->cand2d_n.p, 0, sizeof(int32_t), st));
+      if (t->d == 4)
+        sweep2d_select_kernel<4, 0><<<(unsigned)div_up(items, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, par, nullptr,
+                                                                               (const Sweep2dFilter *)R->filt2d.p, (int)n_obs, R->cand2d.p, R->cand2d_n.p);
+      else
+        sweep2d_select_kernel<2, 0><<<(unsigned)div_up(items, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, par, nullptr,
+                                                                               (const Sweep2dFilter *)R->filt2d.p, (int)n_obs, R->cand2d.p, R->cand2d_n.p);
+      post_launch(ctx);
+      cand = R->cand2d.p;
+      n_cand = R->cand2d_n.p;
+      blocks = (unsigned)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * SWEEP2D_MINB);
+    }
 #define RQ_ADD2D(D_)                                                                                                   \
   add_sweep_2d_kernel<D_><<<blocks, 256, 0, st>>>(Pg->view(), t->pos.p, E->n_nodes, E->src.p, E->dst.p, E->n_edges, par, \
                                                   E->d_traj_ptr, E->d_traj_xy, R->ids_stage2.p,                        \
                                                   (const Sweep2dFilter *)R->filt2d.p, (int)n_obs, robot_radius,        \
-                                                  rho_coarse, R->edge_flag.p, R->node_flag.p)
+                                                  rho_coarse, R->edge_flag.p, R->node_flag.p, cand, n_cand)
     if (t->d == 4) RQ_ADD2D(4); else RQ_ADD2D(2);
 #undef RQ_ADD2D
     post_launch(ctx);
@@ -293,12 +353,30 @@ void obstacle_remove_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *Pg, int32_t 
   sweep_prepare_result(E, R);
   if (E->n_edges > 0) {
     const double rho_coarse = robot_radius + 2 * min_turn_radius;
-    const unsigned blocks = (unsigned)div_up(E->n_edges * 32, 256);
+    // the removed obstacle's filter admits a few per cent of the edges: list them first, then persistent warps
+    const bool two_stage = E->n_edges < ((int64_t)1 << 31);
+    const int32_t *cand = nullptr, *n_cand = nullptr;
+    unsigned blocks = (unsigned)div_up(E->n_edges * 32, 256);
+    if (two_stage) {
+      R->cand2d.ensure((size_t)E->n_edges + 1, st);
+      R->cand2d_n.ensure(4, st);
+      RQ_CUDA(cudaMemsetAsync(R->cand2d_n.p, 0, sizeof(int32_t), st));
+      if (t->d == 4)
+        sweep2d_select_kernel<4, 1><<<(unsigned)div_up(E->n_edges, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, nullptr, dinf,
+                                                                                    (const Sweep2dFilter *)R->filt2d.p, 1, R->cand2d.p, R->cand2d_n.p);
+      else
+        sweep2d_select_kernel<2, 1><<<(unsigned)div_up(E->n_edges, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, nullptr, dinf,
+                                                                                    (const Sweep2dFilter *)R->filt2d.p, 1, R->cand2d.p, R->cand2d_n.p);
+      post_launch(ctx);
+      cand = R->cand2d.p;
+      n_cand = R->cand2d_n.p;
+      blocks = (unsigned)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * SWEEP2D_MINB);
+    }
 #define RQ_REM2D(D_)                                                                                                  \
   remove_sweep_2d_kernel<D_><<<blocks, 256, 0, st>>>(Pg->view(), t->pos.p, E->src.p, E->dst.p, E->n_edges, dinf,     \
                                                      E->d_traj_ptr, E->d_traj_xy, R->ids_stage2.p,                   \
                                                      (const Sweep2dFilter *)R->filt2d.p, (int)ids.size(),            \
-                                                     robot_radius, rho_coarse, R->edge_flag.p, R->node_flag.p)
+                                                     robot_radius, rho_coarse, R->edge_flag.p, R->node_flag.p, cand, n_cand)
     if (t->d == 4) RQ_REM2D(4); else RQ_REM2D(2);
 #undef RQ_REM2D
     post_launch(ctx);
