@@ -472,6 +472,7 @@ def main():
     ap.add_argument("--radius", type=float, default=None)
     ap.add_argument("--occupancy", type=float, default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-count-gather", action="store_true", help="diagnosis: skip the per-step gather of the counts (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-c1", action="store_true")
@@ -531,7 +532,7 @@ def main():
 
     def step():
         _, total = tree.range_query(dq, r, want_dist=True, result=res, n_queries=args.queries)
-        if world > 1:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink, inside the
+        if world > 1 and not args.no_count_gather:   # fixed-size result gather: per-query counts of every rank (NCCL over NVLink, inside the
             # library, on its side stream: the next step's kernel does not wait for it)
             comm.allgather([res.device_pointers()[0]], [gathered.data_ptr()], args.queries * 4, side_stream=True)
         return total

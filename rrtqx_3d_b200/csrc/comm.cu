@@ -23,6 +23,7 @@ struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;   // optional
   ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -47,6 +48,7 @@ static NcclApi &nccl_api() {
   };
   api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(h, "ncclCommInitRankConfig");
   api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
   api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
@@ -195,7 +197,19 @@ rrtqx_status rrtqx_comm_init_rank(rrtqx_ctx *ctx, const void *id128, int32_t ran
       ncclUniqueId id;
       memcpy(&id, id128, sizeof(id));
       RQ_CUDA(cudaSetDevice(ctx->device));
-      RQ_NCCL(nccl_api().CommInitRank(&c->nccl[0], n_ranks, id, rank));
+      // RRTQX_NCCL_MAX_CTAS > 0 caps the CTAs NCCL may use (diagnosis: the gathers share the GPU with persistent
+      // kernels that own every SM).  Measured on 8 B200s (scripts/exp_scale8.sh): caps of 1, 2, 4 make the C2 step
+      // 1.4-3 % and the sharded edge batch 27-135 % slower than NCCL's default, so the default is no cap.  The config
+      // struct of the compile-time header is accepted by newer NCCL builds (its size / version fields exist for that).
+      NcclApi &N = nccl_api();
+      if (N.CommInitRankConfig && ctx->tune.nccl_max_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = ctx->tune.nccl_max_ctas;
+        RQ_NCCL(N.CommInitRankConfig(&c->nccl[0], n_ranks, id, rank, &cfg));
+      } else {
+        RQ_NCCL(N.CommInitRank(&c->nccl[0], n_ranks, id, rank));
+      }
     }
     *out = c;
   });

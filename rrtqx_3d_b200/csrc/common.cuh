@@ -114,6 +114,7 @@ struct Tuning {
   int fused_variant = -1;        // < 0: chosen from the expected neighbour count
   int range_kernel = 5, v5_nw = 24, qsort_s = 3, qsort_f = 1;
   unsigned v5_unit = 0;          // 0: V5_UNIT
+  int nccl_max_ctas = 0;         // cap on the CTAs NCCL may use for this library's gathers (0: NCCL's default; caps of 1-4 measured slower on 8 B200s)
   double grid_occupancy = 0.0, grid_aspect = 0.0;  // 0: the tree's defaults
   void load() {
     *this = Tuning();
@@ -132,6 +133,7 @@ struct Tuning {
     v5_nw = (int)geti("RRTQX_V5_NW", 24);
     const long long u = geti("RRTQX_V5_UNIT", 0);
     v5_unit = (unsigned)(u > 0 ? u : 0);
+    nccl_max_ctas = (int)geti("RRTQX_NCCL_MAX_CTAS", 0);
     const long long s = geti("RRTQX_QSORT_S", 3), f = geti("RRTQX_QSORT_F", 1);
     qsort_s = (int)(s < 1 ? 1 : (s > 16 ? 16 : s));
     qsort_f = (int)(f < 1 ? 1 : (f > 8 ? 8 : f));
