@@ -396,7 +396,8 @@ def c4_dubins(ctx, n_edges, steps):
     sweep_2d = {"nodes": len(nodes4), "edges": int(len(srcn)), "trajectory_rows": int(rows4), "obstacles": int(len(all_obs)),
                 "solve_trajectories_ms_wall": solve_all_ms, "ms": float(np.mean(sw_ms)),
                 "edges_per_s": len(srcn) / (float(np.mean(sw_ms)) / 1e3), "blocked_edges": int(blocked4),
-                "orphans": int(orphans4), "single_obstacle_ms": float(np.mean(one_ms)),
+                "orphans": int(orphans4), "single_obstacle_ms": float(np.median(one_ms)),
+                "single_obstacle_ms_each": [round(float(x), 4) for x in one_ms],
                 "note": "addNewObstacle of the Otte generation with DubinsEdge: theta-wrapped start-node filter, "
                         "sampled-trajectory check of every out-edge and parent edge of the candidates"}
     sw.close()

@@ -270,6 +270,8 @@ static void sweep2d_prepare(rrtqx_edges *E, const rrtqx_polygons *Pg, const int3
   for (int64_t i = 0; i < n_ids; ++i) RQ_REQUIRE(ids_host[i] >= 0 && ids_host[i] < Pg->n, "obstacle id out of range");
   R->ids_stage2.ensure((size_t)n_ids + 1, st);
   R->filt2d.ensure((size_t)n_ids * sizeof(Sweep2dFilter) + 16, st);
+  R->cand2d.ensure((size_t)items + 1, st);   // candidate list of the two-stage form (grow-only: allocated once per graph size)
+  R->cand2d_n.ensure(4, st);
   if (n_ids) {
     RQ_CUDA(cudaMemcpyAsync(R->ids_stage2.p, ids_host, sizeof(int32_t) * n_ids, cudaMemcpyHostToDevice, st));
     RQ_CUDA(cudaStreamSynchronize(st));  // ids_host may be a temporary of the caller
@@ -304,8 +306,6 @@ void obstacle_add_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *Pg, const int32
     const int32_t *cand = nullptr, *n_cand = nullptr;
     unsigned blocks = (unsigned)div_up(items * 32, 256);
     if (two_stage) {
-      R->cand2d.ensure((size_t)items + 1, st);
-      R->cand2d_n.ensure(4, st);
       RQ_CUDA(cudaMemsetAsync(R->cand2d_n.p, 0, sizeof(int32_t), st));
       if (t->d == 4)
         sweep2d_select_kernel<4, 0><<<(unsigned)div_up(items, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, par, nullptr,
@@ -358,8 +358,6 @@ void obstacle_remove_sweep_2d(rrtqx_edges *E, const rrtqx_polygons *Pg, int32_t 
     const int32_t *cand = nullptr, *n_cand = nullptr;
     unsigned blocks = (unsigned)div_up(E->n_edges * 32, 256);
     if (two_stage) {
-      R->cand2d.ensure((size_t)E->n_edges + 1, st);
-      R->cand2d_n.ensure(4, st);
       RQ_CUDA(cudaMemsetAsync(R->cand2d_n.p, 0, sizeof(int32_t), st));
       if (t->d == 4)
         sweep2d_select_kernel<4, 1><<<(unsigned)div_up(E->n_edges, 256), 256, 0, st>>>(t->pos.p, E->n_nodes, E->src.p, E->n_edges, nullptr, dinf,
