@@ -271,17 +271,28 @@ __global__ void cell_scatter_kernel(const int32_t *__restrict__ cell_id, int64_t
   sperm[slot] = (int32_t)i;
 }
 
-// Deterministic layout: inside a cell, ascending node index.
-__global__ void cell_sort_kernel(const int32_t *__restrict__ cell_start, int ncell, int32_t *__restrict__ sperm) {
+// Deterministic layout: inside a cell, ascending x (ties: ascending node index).  cell_of() is monotone in x, so a
+// whole ROW of cells is then sorted by x: the neighbours of a query in a row are one nearly contiguous run of slots
+// (fewer 128-byte lines per 32 gathered exact records in the range kernel's flush).  No kernel relies on the order
+// inside a cell for its result.
+#ifndef RRTQX_CELL_ORDER_X
+#define RRTQX_CELL_ORDER_X 1
+#endif
+__global__ void cell_sort_kernel(const int32_t *__restrict__ cell_start, int ncell, const double4 *__restrict__ pos,
+                                 int32_t *__restrict__ sperm) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int a = cell_start[c], b = cell_start[c + 1];
   if (b - a > 256) return;  // degenerate pile-up: order left as scattered (result sets unaffected)
   for (int i = a + 1; i < b; ++i) {
-    int v = sperm[i];
+    const int v = sperm[i];
+    const double xv = RRTQX_CELL_ORDER_X ? pos[v].x : 0.0;
     int j = i - 1;
-    while (j >= a && sperm[j] > v) {
-      sperm[j + 1] = sperm[j];
+    while (j >= a) {
+      const int u = sperm[j];
+      const double xu = RRTQX_CELL_ORDER_X ? pos[u].x : 0.0;
+      if (!(xu > xv || (xu == xv && u > v))) break;   // NaN x: compares false, keeps its place
+      sperm[j + 1] = u;
       --j;
     }
     sperm[j + 1] = v;
@@ -418,7 +429,7 @@ void tree_reindex(rrtqx_tree *t) {
   exclusive_scan<int32_t, int32_t>(ctx, t->cell_cursor.p, ncell, t->cell_start.p, t->scan_tmp);
   RQ_CUDA(cudaMemsetAsync(t->cell_cursor.p, 0, sizeof(int32_t) * ((size_t)ncell + 1), st));
   cell_scatter_kernel<<<div_up(n, TB), TB, 0, st>>>(t->cell_id.p, n, t->cell_start.p, t->cell_cursor.p, t->sperm.p);
-  cell_sort_kernel<<<div_up(ncell, TB), TB, 0, st>>>(t->cell_start.p, ncell, t->sperm.p);
+  cell_sort_kernel<<<div_up(ncell, TB), TB, 0, st>>>(t->cell_start.p, ncell, t->pos.p, t->sperm.p);
   cell_gather_kernel<<<div_up(n + 8, TB), TB, 0, st>>>(t->pos.p, t->sperm.p, n, t->d, t->lo[0], t->lo[1], t->lo[2], t->sx.p, t->sy.p,
                                                    t->sz.p, t->sw.p, t->f4.p, t->d4.p, t->fmaxabs.p);
   post_launch(ctx, 3);

@@ -611,3 +611,45 @@ def test_resident_edge_check_equals_batch_check_and_oracle(ctx):
             del os.environ["RRTQX_NO_ITEM_GRID"]
             ctx.reload_tuning()
         assert np.array_equal(one[0], want[0]) and np.array_equal(one[1], want[1])
+
+
+@pytest.mark.gpu
+def test_sweep_result_is_reusable_and_its_flag_view_matches_the_lists(ctx):
+    """The flag compaction cleans the flag arrays behind itself and rrtqx_sweep_result_flags rebuilds the byte view from
+    the id lists: one result object reused across sweeps (different obstacle subsets, flag view read in between, a
+    larger edge set afterwards) must give what fresh result objects give."""
+    from rrtqx_3d_b200.device import SweepResult
+    pts, _, _ = W.c2_workload(20000, 1)
+    t, src, dst, parent = _neighbour_graph(ctx, pts, 2.0)
+    centers, radii = W.c3_obstacles(12)
+    S = SphereSet(ctx, centers, radii)
+    E = EdgeSet(t)
+    E.upload(src, dst, parent)
+    reused = SweepResult(ctx)
+    for ids in ([0], [3, 4, 5], list(range(12)), [7], [], [1]):
+        ids = np.asarray(ids, dtype=np.int32)
+        fresh = E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA)
+        fe, fn = fresh.fetch()
+        E.add_sweep(S, ids, W.ROBOT_RADIUS, W.DELTA, result=reused)
+        ge, gn = reused.fetch()
+        assert np.array_equal(ge, fe) and np.array_equal(gn, fn)
+        assert np.all(np.diff(ge) > 0) and np.all(np.diff(gn) > 0)          # ascending id lists
+        for _ in range(2):                                                     # the view can be read repeatedly
+            ef, nf = reused.flags(len(src), len(pts))
+            assert np.array_equal(np.flatnonzero(ef), ge) and np.array_equal(np.flatnonzero(nf), gn)
+            assert set(np.unique(ef)) <= {0, 1} and set(np.unique(nf)) <= {0, 1}
+    # remove sweep through the same object, then a LARGER edge set (flag arrays grow: new allocation, zeroed)
+    first = E.add_sweep(S, np.arange(12, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA)
+    inf = np.zeros(len(src), dtype=np.uint8)
+    inf[first.fetch()[0]] = 1
+    others = np.arange(1, 12, dtype=np.int32)
+    want = E.remove_sweep(S, 0, others, inf, W.ROBOT_RADIUS, W.DELTA).fetch()
+    got = E.remove_sweep(S, 0, others, inf, W.ROBOT_RADIUS, W.DELTA, result=reused).fetch()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    t2, src2, dst2, parent2 = _neighbour_graph(ctx, pts, 2.3)
+    assert len(src2) > len(src)
+    E2 = EdgeSet(t2)
+    E2.upload(src2, dst2, parent2)
+    w2 = E2.add_sweep(S, np.arange(12, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA).fetch()
+    g2 = E2.add_sweep(S, np.arange(12, dtype=np.int32), W.ROBOT_RADIUS, W.DELTA, result=reused).fetch()
+    assert np.array_equal(g2[0], w2[0]) and np.array_equal(g2[1], w2[1])
