@@ -112,7 +112,7 @@ struct Tuning {
        nearest_warp = false, no_item_grid = false;
   int64_t cover_min_items = -1;  // < 0: the measured break-even defaults
   int fused_variant = -1;        // < 0: chosen from the expected neighbour count
-  int range_kernel = 5, v5_nw = 24, qsort_s = 3, qsort_f = 1;
+  int range_kernel = 5, v5_nw = 24, qsort_s = 2, qsort_f = 1;   // supercells of 2^3 cells with the 2:1 grid aspect (scripts/tune_v5.sh)
   unsigned v5_unit = 0;          // 0: V5_UNIT
   int nccl_max_ctas = 0;         // cap on the CTAs NCCL may use for this library's gathers (0: NCCL's default; caps of 1-4 measured slower on 8 B200s)
   double grid_occupancy = 0.0, grid_aspect = 0.0;  // 0: the tree's defaults
@@ -134,7 +134,7 @@ struct Tuning {
     const long long u = geti("RRTQX_V5_UNIT", 0);
     v5_unit = (unsigned)(u > 0 ? u : 0);
     nccl_max_ctas = (int)geti("RRTQX_NCCL_MAX_CTAS", 0);
-    const long long s = geti("RRTQX_QSORT_S", 3), f = geti("RRTQX_QSORT_F", 1);
+    const long long s = geti("RRTQX_QSORT_S", 2), f = geti("RRTQX_QSORT_F", 1);
     qsort_s = (int)(s < 1 ? 1 : (s > 16 ? 16 : s));
     qsort_f = (int)(f < 1 ? 1 : (f > 8 ? 8 : f));
     const double o = getd("RRTQX_GRID_OCCUPANCY"), a = getd("RRTQX_GRID_ASPECT");

@@ -64,7 +64,7 @@ struct rrtqx_tree {
   int64_t n = 0;         // tree size
   int64_t n_sorted = 0;  // covered by the grid index
   double occupancy = 4.0;
-  double aspect = 1.0;   // cell width across rows / cell length along x
+  double aspect = 2.0;   // cell width across rows / cell length along x (C2 sweep, scripts/tune_v5.sh: 1 / 1.5 / 2 / 3 / 4 -> 2.77 / 2.73 / 2.70 / 2.70 / 2.73 ms; 2 keeps kdFindNearest at 0.34 ms)
   int64_t tail_limit = 4096;
   rrtqx::ScratchMap scratch;  // per-tree scratch (nearest-query sort buffers, extend_query state)
 
