@@ -67,7 +67,12 @@ typedef struct rrtqx_sweep_result rrtqx_sweep_result;
 
 RRTQX_API const char *rrtqx_version(void);
 /* device: CUDA ordinal.  cuda_stream: a cudaStream_t to launch on (e.g. the
- * caller's current stream) or NULL for a private non-blocking stream. */
+ * caller's current stream) or NULL for a private non-blocking stream.  The
+ * handle of CUDA's DEFAULT stream is 0 == NULL: a caller that wants its own
+ * work ordered with the library's (timing events, cache flushes, tensors it
+ * fills before a call) must hand over a stream it created, not the default
+ * one (PyTorch: torch.cuda.Stream(), not torch.cuda.current_stream() of a
+ * fresh process, whose cuda_stream is 0). */
 RRTQX_API rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream,
                                         rrtqx_ctx **out);
 RRTQX_API rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx);
