@@ -12,6 +12,7 @@
 // one otherwise), so the library itself has no link-time dependency on it and single-GPU users never touch it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <vector>
 
@@ -80,6 +81,25 @@ struct rrtqx_comm {
   std::vector<DevBuf<uint8_t> *> flag;
   std::vector<DevBuf<unsigned long long> *> peers;
   std::vector<std::vector<unsigned long long>> peers_host;  // what `peers` holds (uploaded only when it changes)
+  // One-process-per-GPU form on ONE node: a result window per rank, mapped into every other rank's address space
+  // through CUDA IPC.  A gather is then peer copies (copy engines, no SM) or the packing kernel's own stores straight
+  // into every window, one epoch word per (destination, source) pair, and a local copy out of the own window --
+  // no collective kernel that would share the SMs with the persistent range kernel.
+  struct Ipc {
+    bool on = false;
+    size_t cap = 0;                           // bytes per slot; two slots alternate by epoch (double buffering)
+    unsigned char *win = nullptr;             // own window [2][cap]
+    unsigned long long *flags = nullptr;      // own epoch words [2][n_ranks]
+    std::vector<unsigned char *> peer_win;    // [n_ranks], own entry = win
+    std::vector<unsigned long long *> peer_flags;
+    DevBuf<unsigned long long> d_peer_win, d_peer_flags;   // the same pointers on the device (for the kernels)
+    DevBuf<unsigned int> counter;                         // blocks of the gather kernel that have finished (self-resetting)
+    unsigned long long epoch = 0;
+    // the epochs of a rank form ONE sequence whatever stream carries them (the double buffering relies on it): an
+    // operation queued on another stream than its predecessor first waits for that predecessor
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev_last = nullptr;
+  } ipc;
 };
 
 namespace rrtqx {
@@ -88,7 +108,7 @@ namespace rrtqx {
 // its peers'): the gather of the sharded check is this kernel's store, not a collective.
 __global__ void __launch_bounds__(256)
 pack_scatter_kernel(const uint8_t *__restrict__ flag, int64_t n_flags, int64_t word0, int64_t n_words,
-                    const unsigned long long *__restrict__ dests, int n_dest) {
+                    const unsigned long long *__restrict__ dests, int n_dest, unsigned long long dest_byte_offset) {
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_words) return;
   const int64_t base = w * 32;
@@ -103,7 +123,84 @@ pack_scatter_kernel(const uint8_t *__restrict__ flag, int64_t n_flags, int64_t w
   } else {
     for (int j = 0; j < 32 && base + j < n_flags; ++j) word |= flag[base + j] ? (1u << j) : 0u;
   }
-  for (int r = 0; r < n_dest; ++r) reinterpret_cast<unsigned *>(dests[r])[word0 + w] = word;
+  for (int r = 0; r < n_dest; ++r) reinterpret_cast<unsigned *>(dests[r] + dest_byte_offset)[word0 + w] = word;
+}
+
+// Epoch words of the IPC windows, one launch behind the copies / the packing kernel on the same stream: thread j
+// tells rank j that this rank's part of epoch e has landed in its window (system-scope release store), then waits
+// until rank j has said so for this rank's window.  Every rank signals before it waits, so there is no cycle.  The
+// wait is bounded (about 10 s): a dead peer must not hang the GPU; the next call reports it through *timed_out.
+__global__ void ipc_exchange_kernel(const unsigned long long *__restrict__ peer_flags, const unsigned long long *__restrict__ flags,
+                                    int n_ranks, int slot, int rank, unsigned long long epoch, int32_t *__restrict__ timed_out) {
+  const int j = threadIdx.x;
+  if (j >= n_ranks) return;
+  __threadfence_system();
+  unsigned long long *f = reinterpret_cast<unsigned long long *>(peer_flags[j]) + (size_t)slot * n_ranks + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + (size_t)slot * n_ranks + j) : "memory");
+    if (v >= epoch) break;
+    __nanosleep(100);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) { *timed_out = 1; break; }
+  }
+  __threadfence_system();
+}
+
+
+// The gather of one rank's part in ONE launch: a few small blocks (128 threads, <= 32 registers: they fit next to a
+// resident block of the persistent range kernel) store the part into slot `slot` of EVERY rank's window over NVLink;
+// the last block to finish runs the epoch exchange above.  (Eight cudaMemcpyAsync calls instead cost 40 us of host
+// time per step at N = 8 -- more than the NCCL call they replaced.)
+__global__ void __launch_bounds__(128, 16)
+ipc_gather_kernel(const unsigned char *__restrict__ send, size_t bytes, const unsigned long long *__restrict__ peer_win,
+                  size_t dst_offset, int n_ranks, unsigned int *__restrict__ counter,
+                  const unsigned long long *__restrict__ peer_flags, const unsigned long long *__restrict__ flags, int slot,
+                  int rank, unsigned long long epoch, int32_t *__restrict__ timed_out) {
+  __shared__ int s_last;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)send | bytes | dst_offset) & 15u) == 0) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(send);
+    for (size_t i = tid; i < bytes / 16; i += nthr) {
+      const uint4 v = src[i];
+      for (int j = 0; j < n_ranks; ++j) reinterpret_cast<uint4 *>(peer_win[j] + dst_offset)[i] = v;
+    }
+  } else {
+    for (size_t i = tid; i < bytes; i += nthr) {
+      const unsigned char v = send[i];
+      for (int j = 0; j < n_ranks; ++j) reinterpret_cast<unsigned char *>(peer_win[j] + dst_offset)[i] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    s_last = prev == gridDim.x - 1;
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  const int j = threadIdx.x;
+  if (j >= n_ranks) return;
+  __threadfence_system();
+  unsigned long long *f = reinterpret_cast<unsigned long long *>(peer_flags[j]) + (size_t)slot * n_ranks + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + (size_t)slot * n_ranks + j) : "memory");
+    if (v >= epoch) break;
+    __nanosleep(100);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) { *timed_out = 1; break; }
+  }
+  __threadfence_system();
 }
 
 }  // namespace rrtqx
@@ -140,6 +237,123 @@ rrtqx_comm *new_comm(int n_ranks, int n_local, int rank0, rrtqx_ctx *const *ctxs
     c->peers_host.emplace_back();
   }
   return c;
+}
+
+void ipc_teardown(rrtqx_comm *c) {
+  rrtqx_comm::Ipc &I = c->ipc;
+  const int me = c->rank0;
+  for (size_t j = 0; j < I.peer_win.size(); ++j) {
+    if ((int)j == me) continue;
+    if (I.peer_win[j]) cudaIpcCloseMemHandle(I.peer_win[j]);
+    if (I.peer_flags[j]) cudaIpcCloseMemHandle(I.peer_flags[j]);
+  }
+  if (I.win) cudaFree(I.win);
+  if (I.flags) cudaFree(I.flags);
+  I.win = nullptr; I.flags = nullptr;
+  if (I.ev_last) { cudaEventDestroy(I.ev_last); I.ev_last = nullptr; }
+  I.last_stream = nullptr;
+  I.peer_win.clear(); I.peer_flags.clear();
+  I.on = false;
+  cudaGetLastError();
+}
+
+// Collective over the ranks of a one-process-per-GPU communicator: allocate the window, exchange the IPC handles
+// through NCCL, map the peers' windows.  Every rank ends with the same answer (a second exchange agrees on it); on
+// "no" the windows are released and the gathers stay on NCCL.
+void ipc_setup(rrtqx_comm *c, size_t cap) {
+  rrtqx_ctx *ctx = c->ctx[0];
+  cudaStream_t st = ctx->stream;
+  rrtqx_comm::Ipc &I = c->ipc;
+  const int G = c->n_ranks, me = c->rank0;
+  NcclApi &N = nccl_api();
+  struct Card { cudaIpcMemHandle_t win, flags; char host[64]; int32_t ok, device; unsigned char pad[56]; };
+  static_assert(sizeof(Card) == 256, "IPC exchange card");
+  Card mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.device = ctx->device;
+  gethostname(mine.host, sizeof(mine.host) - 1);
+  bool ok = true;
+  if (cudaMalloc((void **)&I.win, 2 * cap) != cudaSuccess) ok = false;
+  if (ok && cudaMalloc((void **)&I.flags, 2 * sizeof(unsigned long long) * (size_t)G) != cudaSuccess) ok = false;
+  if (ok) ok = cudaMemset(I.flags, 0, 2 * sizeof(unsigned long long) * (size_t)G) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.win, I.win) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, I.flags) == cudaSuccess;
+  cudaGetLastError();
+  mine.ok = ok ? 1 : 0;
+  DevBuf<unsigned char> stage;
+  stage.ensure(sizeof(Card) * (size_t)G, st);
+  std::vector<Card> all((size_t)G);
+  auto exchange = [&]() {
+    RQ_CUDA(cudaMemcpyAsync(stage.p + sizeof(Card) * (size_t)me, &mine, sizeof(Card), cudaMemcpyHostToDevice, st));
+    RQ_NCCL(N.AllGather(stage.p + sizeof(Card) * (size_t)me, stage.p, sizeof(Card), ncclUint8, c->nccl[0], st));
+    RQ_CUDA(cudaMemcpyAsync(all.data(), stage.p, sizeof(Card) * (size_t)G, cudaMemcpyDeviceToHost, st));
+    RQ_CUDA(cudaStreamSynchronize(st));
+  };
+  exchange();
+  for (int j = 0; j < G; ++j) ok = ok && all[j].ok && strncmp(all[j].host, mine.host, sizeof(mine.host)) == 0;
+  I.peer_win.assign((size_t)G, nullptr);
+  I.peer_flags.assign((size_t)G, nullptr);
+  if (ok) {
+    for (int j = 0; j < G && ok; ++j) {
+      if (j == me) { I.peer_win[j] = I.win; I.peer_flags[j] = I.flags; continue; }
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->device, all[j].device) != cudaSuccess || !can) { ok = false; break; }
+      void *pw = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pw, all[j].win, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      I.peer_win[j] = (unsigned char *)pw;
+      if (cudaIpcOpenMemHandle(&pf, all[j].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      I.peer_flags[j] = (unsigned long long *)pf;
+    }
+    cudaGetLastError();
+  }
+  mine.ok = ok ? 1 : 0;
+  exchange();   // agree: a window is used only if EVERY rank mapped every window
+  for (int j = 0; j < G; ++j) ok = ok && all[j].ok;
+  if (!ok) { ipc_teardown(c); return; }
+  std::vector<unsigned long long> pw((size_t)G), pf((size_t)G);
+  for (int j = 0; j < G; ++j) { pw[j] = (unsigned long long)(uintptr_t)I.peer_win[j]; pf[j] = (unsigned long long)(uintptr_t)I.peer_flags[j]; }
+  I.d_peer_win.ensure((size_t)G, st);
+  I.d_peer_flags.ensure((size_t)G, st);
+  I.counter.ensure(4, st);
+  RQ_CUDA(cudaMemsetAsync(I.counter.p, 0, 4 * sizeof(unsigned int), st));
+  RQ_CUDA(cudaMemcpyAsync(I.d_peer_win.p, pw.data(), sizeof(unsigned long long) * (size_t)G, cudaMemcpyHostToDevice, st));
+  RQ_CUDA(cudaMemcpyAsync(I.d_peer_flags.p, pf.data(), sizeof(unsigned long long) * (size_t)G, cudaMemcpyHostToDevice, st));
+  RQ_CUDA(cudaStreamSynchronize(st));
+  I.cap = cap;
+  I.epoch = 0;
+  I.on = true;
+}
+
+// start of an IPC gather on stream s: order it behind the previous one, draw the epoch and its slot
+unsigned long long ipc_begin(rrtqx_comm *c, cudaStream_t s, int *slot) {
+  rrtqx_comm::Ipc &I = c->ipc;
+  if (!I.ev_last) RQ_CUDA(cudaEventCreateWithFlags(&I.ev_last, cudaEventDisableTiming));
+  if (I.last_stream && I.last_stream != s) RQ_CUDA(cudaStreamWaitEvent(s, I.ev_last, 0));
+  const unsigned long long e = ++I.epoch;
+  *slot = (int)(e & 1ull);
+  return e;
+}
+
+// a wait that ran into its 10 s bound (dead or wedged peer) fails the NEXT call on the communicator
+void ipc_check(rrtqx_comm *c) {
+  if (!c->ipc.on) return;
+  HostMail &M = host_mail(c->ctx[0]);
+  if (*(volatile int32_t *)&M.h->aux[1]) {
+    M.h->aux[1] = 0;
+    throw Error(RRTQX_ERR_CUDA, "a rank did not publish its part of a gather within 10 s (IPC window)");
+  }
+}
+
+// Behind the writers of epoch e on stream s (peer copies or the packing kernel): publish, wait for every rank's part,
+// copy the own window out.  Returns nothing; a timed-out wait is reported by ipc_check().
+void ipc_finish(rrtqx_comm *c, cudaStream_t s, int slot, unsigned long long e, void *recv, size_t total_bytes) {
+  rrtqx_comm::Ipc &I = c->ipc;
+  const int G = c->n_ranks;
+  HostMail &M = host_mail(c->ctx[0]);
+  ipc_exchange_kernel<<<1, 32, 0, s>>>(I.d_peer_flags.p, I.flags, G, slot, c->rank0, e, &M.d->aux[1]);
+  RQ_CUDA(cudaMemcpyAsync(recv, I.win + (size_t)slot * I.cap, total_bytes, cudaMemcpyDeviceToDevice, s));
+  RQ_CUDA(cudaEventRecord(I.ev_last, s));
+  I.last_stream = s;
+  post_launch(c->ctx[0], 1);
 }
 }  // namespace
 
@@ -210,6 +424,7 @@ rrtqx_status rrtqx_comm_init_rank(rrtqx_ctx *ctx, const void *id128, int32_t ran
       } else {
         RQ_NCCL(N.CommInitRank(&c->nccl[0], n_ranks, id, rank));
       }
+      if (!ctx->tune.comm_no_ipc && n_ranks <= 32) ipc_setup(c, (size_t)ctx->tune.comm_ipc_mb << 20);
     }
     *out = c;
   });
@@ -217,6 +432,11 @@ rrtqx_status rrtqx_comm_init_rank(rrtqx_ctx *ctx, const void *id128, int32_t ran
 
 rrtqx_status rrtqx_comm_destroy(rrtqx_comm *c) {
   if (!c) return RRTQX_OK;
+  if (c->ipc.win) {
+    if (handle_live(c->ctx[0])) { cudaSetDevice(c->ctx[0]->device); cudaStreamSynchronize(c->ctx[0]->stream); }
+    cudaStreamSynchronize(c->side[0]);
+    ipc_teardown(c);
+  }
   for (int i = 0; i < c->n_local; ++i) {
     if (handle_live(c->ctx[i])) cudaSetDevice(c->ctx[i]->device);
     cudaStreamSynchronize(c->side[i]);
@@ -238,7 +458,7 @@ rrtqx_status rrtqx_comm_info(const rrtqx_comm *c, int32_t *n_ranks, int32_t *n_l
   if (n_ranks) *n_ranks = c->n_ranks;
   if (n_local) *n_local = c->n_local;
   if (first_rank) *first_rank = c->rank0;
-  if (peer_stores) *peer_stores = c->p2p ? 1 : 0;
+  if (peer_stores) *peer_stores = (c->p2p || c->ipc.on) ? 1 : 0;
   if (nccl_version) {
     *nccl_version = 0;
     if (c->n_ranks > 1) { int v = 0; if (nccl_api().GetVersion(&v) == ncclSuccess) *nccl_version = v; }
@@ -264,6 +484,33 @@ rrtqx_status rrtqx_comm_allgather(rrtqx_comm *c, const void *const *send, void *
     if (c->n_ranks == 1) {
       RQ_CUDA(cudaSetDevice(c->ctx[0]->device));
       if (send[0] != recv[0]) RQ_CUDA(cudaMemcpyAsync(recv[0], send[0], (size_t)bytes_per_rank, cudaMemcpyDeviceToDevice, c->ctx[0]->stream));
+      return;
+    }
+    ipc_check(c);
+    if (c->ipc.on && c->n_local == 1 && (size_t)bytes_per_rank * (size_t)c->n_ranks <= c->ipc.cap) {
+      // copy engines: this rank's part goes into slot (epoch & 1) of every rank's window, then epoch words, then the
+      // own window is copied out -- no kernel of a collective library on the SMs
+      rrtqx_comm::Ipc &I = c->ipc;
+      rrtqx_ctx *ctx = c->ctx[0];
+      RQ_CUDA(cudaSetDevice(ctx->device));
+      cudaStream_t s = ctx->stream;
+      if (on_side_stream) {
+        RQ_CUDA(cudaEventRecord(c->ev_main[0], ctx->stream));
+        RQ_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_main[0], 0));
+        s = c->side[0];
+      }
+      int slot = 0;
+      const unsigned long long e = ipc_begin(c, s, &slot);
+      HostMail &M = host_mail(ctx);
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(32, bytes_per_rank / (16 * 128)));
+      ipc_gather_kernel<<<blocks, 128, 0, s>>>((const unsigned char *)send[0], (size_t)bytes_per_rank, I.d_peer_win.p,
+                                               (size_t)slot * I.cap + (size_t)c->rank0 * (size_t)bytes_per_rank, c->n_ranks,
+                                               I.counter.p, I.d_peer_flags.p, I.flags, slot, c->rank0, e, &M.d->aux[1]);
+      RQ_CUDA(cudaMemcpyAsync(recv[0], I.win + (size_t)slot * I.cap, (size_t)bytes_per_rank * (size_t)c->n_ranks,
+                              cudaMemcpyDeviceToDevice, s));
+      RQ_CUDA(cudaEventRecord(I.ev_last, s));
+      I.last_stream = s;
+      post_launch(ctx, 1);
       return;
     }
     NcclApi &N = nccl_api();
@@ -313,6 +560,9 @@ rrtqx_status rrtqx_edge_check_batch_sharded(rrtqx_comm *c, rrtqx_tree *const *tr
     // destinations of each rank's words: every local rank's buffer when peers can be stored to directly, otherwise
     // the rank's own buffer (NCCL moves the words afterwards).  Uploaded only when the caller's buffers change.
     const bool direct = c->p2p && L == G && G > 1;
+    // one process per GPU with IPC windows: the packing kernel stores into slot (epoch & 1) of every rank's window
+    const bool ipc_direct = !direct && c->ipc.on && L == 1 && G > 1 && (size_t)per * 4u * (size_t)G <= c->ipc.cap;
+    ipc_check(c);
     for (int i = 0; i < L; ++i) {
       std::vector<unsigned long long> dests;
       if (direct) for (int j = 0; j < L; ++j) dests.push_back((unsigned long long)(uintptr_t)packed_out[j]);
@@ -337,13 +587,23 @@ rrtqx_status rrtqx_edge_check_batch_sharded(rrtqx_comm *c, rrtqx_tree *const *tr
       if (cnt > 0)
         edge_check_launch(ctx, trees[i], spheres[i], src[i] + e0, dst[i] + e0, nullptr, nullptr, cnt, robot_radius, flags,
                           c->flag[i]->p, &bad[i]);
-      if (w1 > w0) {
-        pack_scatter_kernel<<<div_up(w1 - w0, 256), 256, 0, ctx->stream>>>(c->flag[i]->p, cnt, w0, w1 - w0, c->peers[i]->p,
-                                                                           (int)c->peers_host[i].size());
+      unsigned long long e = 0;
+      int slot = 0;
+      if (ipc_direct) e = ipc_begin(c, ctx->stream, &slot);
+      // every word of the rank's shard is written, also the padding words behind the last edge (zero): the gathered
+      // array is then fully defined whatever the caller's buffer or the window held before
+      if (per > 0) {
+        if (ipc_direct)
+          pack_scatter_kernel<<<div_up(per, 256), 256, 0, ctx->stream>>>(c->flag[i]->p, std::max<int64_t>(cnt, 0), per * g, per,
+                                                                         c->ipc.d_peer_win.p, G, (unsigned long long)slot * c->ipc.cap);
+        else
+          pack_scatter_kernel<<<div_up(per, 256), 256, 0, ctx->stream>>>(c->flag[i]->p, std::max<int64_t>(cnt, 0), per * g, per,
+                                                                         c->peers[i]->p, (int)c->peers_host[i].size(), 0ull);
         post_launch(ctx);
       }
+      if (ipc_direct) ipc_finish(c, ctx->stream, slot, e, packed_out[i], (size_t)per * 4u * (size_t)G);
     }
-    if (G > 1 && !direct) {  // in-place all-gather of the equal word shards
+    if (G > 1 && !direct && !ipc_direct) {  // in-place all-gather of the equal word shards
       NcclApi &N = nccl_api();
       RQ_NCCL(N.GroupStart());
       for (int i = 0; i < L; ++i)

@@ -114,6 +114,8 @@ struct Tuning {
   int fused_variant = -1;        // < 0: chosen from the expected neighbour count
   int range_kernel = 5, v5_nw = 24, qsort_s = 2, qsort_f = 1;   // supercells of 2^3 cells with the 2:1 grid aspect (scripts/tune_v5.sh)
   unsigned v5_unit = 0;          // 0: V5_UNIT
+  bool comm_no_ipc = false;      // one process per GPU: gathers through NCCL even where IPC windows are possible
+  int comm_ipc_mb = 64;          // bytes per slot of the IPC result window (two slots per rank), MiB
   int nccl_max_ctas = 0;         // cap on the CTAs NCCL may use for this library's gathers (0: NCCL's default; caps of 1-4 measured slower on 8 B200s)
   double grid_occupancy = 0.0, grid_aspect = 0.0;  // 0: the tree's defaults
   void load() {
@@ -134,6 +136,8 @@ struct Tuning {
     const long long u = geti("RRTQX_V5_UNIT", 0);
     v5_unit = (unsigned)(u > 0 ? u : 0);
     nccl_max_ctas = (int)geti("RRTQX_NCCL_MAX_CTAS", 0);
+    comm_no_ipc = on("RRTQX_COMM_NO_IPC");
+    { const long long mb = geti("RRTQX_COMM_IPC_MB", 64); comm_ipc_mb = (int)(mb < 1 ? 1 : (mb > 4096 ? 4096 : mb)); }
     const long long s = geti("RRTQX_QSORT_S", 2), f = geti("RRTQX_QSORT_F", 1);
     qsort_s = (int)(s < 1 ? 1 : (s > 16 ? 16 : s));
     qsort_f = (int)(f < 1 ? 1 : (f > 8 ? 8 : f));
