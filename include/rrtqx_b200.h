@@ -530,7 +530,12 @@ RRTQX_API rrtqx_status rrtqx_dubins_saturate_batch(rrtqx_ctx *ctx,
  *     NVLink), otherwise NCCL gathers.
  *   rrtqx_comm_init_rank  -- one process per GPU (torchrun): every rank passes
  *     the 128-byte id rank 0 obtained from rrtqx_comm_unique_id (moved between
- *     the processes by the caller), its rank and the rank count.  NCCL gathers.
+ *     the processes by the caller), its rank and the rank count.  Ranks of one
+ *     node map each other's result windows through CUDA IPC (the handles
+ *     travel over NCCL at init) and the gathers become direct stores into the
+ *     peers' windows plus an epoch word per (destination, source); ranks on
+ *     several nodes, RRTQX_COMM_NO_IPC=1 or parts larger than a window slot
+ *     (RRTQX_COMM_IPC_MB, default 64): NCCL gathers.
  * NCCL (libnccl.so.2) is loaded on first use; without it these calls fail with
  * RRTQX_ERR_UNSUPPORTED and nothing else is affected. */
 typedef struct rrtqx_comm rrtqx_comm;
