@@ -22,7 +22,10 @@
 constexpr int V5_TABPAD = 16;  // zero entries behind the last one (a trip group never tests bounds)
 constexpr int V5_UNIT = 128;    // pairs per dynamically scheduled unit of work (a block's warps share one unit; scripts/tune_v5b.sh: 48 / 64 / 96 / 128 / 160 / 256 -> 2.78 / 2.69 / 2.70 / 2.665 / 2.664 / 2.70 ms)
 constexpr int V5_RING = 64;     // published unit bases kept per block
-constexpr int V5_U = 4;        // trips per loop iteration (loads in flight before the first test)
+#ifndef V5_U_TRIPS
+#define V5_U_TRIPS 4
+#endif
+constexpr int V5_U = V5_U_TRIPS;   // trips per loop iteration (loads in flight before the first test)
 
 __device__ __forceinline__ unsigned long long pk2(float a, float b) {
   unsigned long long r;
