@@ -72,7 +72,9 @@ RRTQX_API const char *rrtqx_version(void);
  * work ordered with the library's (timing events, cache flushes, tensors it
  * fills before a call) must hand over a stream it created, not the default
  * one (PyTorch: torch.cuda.Stream(), not torch.cuda.current_stream() of a
- * fresh process, whose cuda_stream is 0). */
+ * fresh process, whose cuda_stream is 0) -- or CUDA's explicit names for the
+ * default streams, cudaStreamLegacy ((void *)0x1) / cudaStreamPerThread
+ * ((void *)0x2), which are non-zero handles and are used verbatim. */
 RRTQX_API rrtqx_status rrtqx_ctx_create(int32_t device, void *cuda_stream,
                                         rrtqx_ctx **out);
 RRTQX_API rrtqx_status rrtqx_ctx_destroy(rrtqx_ctx *ctx);
