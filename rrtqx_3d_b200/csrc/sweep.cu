@@ -520,7 +520,7 @@ remove_sweep_kernel(const double4 *__restrict__ pos, const int32_t *__restrict__
 // the rest to the node array, whose prefix restarts at tiles_a.
 //   * the second kernel ZEROES every flag it found set: the arrays are clean again when the call returns, so the
 //     next call needs no 10 MB memset (rrtqx_sweep_result_flags rebuilds the byte view from the lists);
-//   * a one-warp kernel behind it stores the totals, the sweep statistics (which it zeroes for the next call) and
+//   * its last block to finish stores the totals, the sweep statistics (which it zeroes for the next call) and
 //     one optional extra word (the item grid's overflow flag) into the context's mapped mailbox and publishes the
 //     call number: the host spins on that word instead of three D2H copies and a stream synchronisation.
 constexpr int FC_THREADS = 256, FC_ITEMS = 16, FC_TILE = FC_THREADS * FC_ITEMS;
@@ -642,7 +642,8 @@ static FlagCompactBufs &flag_compact_bufs(rrtqx_ctx *ctx) {
 }
 
 // Flags -> ascending id lists + counts (+ one extra device word, returned in *extra_out).  The lists are allocated
-// for the worst case (every edge / node); three launches back to back, results through the context's mailbox.
+// for the worst case (every edge / node); two launches back to back (tile counts, compaction whose last block
+// publishes), results through the context's mailbox.
 void sweep_finish(rrtqx_ctx *ctx, rrtqx_sweep_result *R, const int32_t *extra_dev, int32_t *extra_out) {
   cudaStream_t st = ctx->stream;
   const int64_t et = (R->n_edges + FC_TILE - 1) / FC_TILE, nt = (R->n_nodes + FC_TILE - 1) / FC_TILE;
